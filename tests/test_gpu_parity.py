@@ -1,0 +1,281 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (include/tsgpu.h),
+against the oracle on the same seeded inputs, against the committed golden vectors of the
+reference binary, and -- at sizes the oracle cannot reach -- through size-independent
+invariants.  Tolerances (BASELINE.json north_star): SNP sequence bit-exact, theta/beta within
+1e-6 relative, held-out log-likelihood within 1e-5."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from conftest import load_case
+
+pytestmark = pytest.mark.gpu
+
+THETA_RTOL = 1e-6
+LL_ATOL = 1e-5
+# what we actually expect: fp64 kernels differ from the sequential reference only by rounding
+TIGHT = 1e-9
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def make_driver(c, **kw):
+    import terastructure_b200 as ts
+    env = ts.Env(c["n"], c["k"], c["l"], seed=c["seed"], rfreq=c["rfreq"])
+    return ts.SNPSamplingE(env, c["rows"], **kw)
+
+
+def test_device_digamma_matches_scipy():
+    """ts_get_elogtheta exposes the device digamma: psi(g) - psi(rowsum) vs SciPy."""
+    import terastructure_b200 as ts
+    from scipy.special import digamma
+    rs = np.random.RandomState(0)
+    n, k = 4096, 5
+    g = np.exp(rs.uniform(np.log(0.02), np.log(5e6), size=(n, k)))
+    e = ts.Engine(n, 8, k)
+    e.load_bed(np.zeros((8, n // 4), np.uint8))
+    e.set_gamma(g)
+    ref = digamma(g) - digamma(g.sum(1, keepdims=True))
+    got = e.elogtheta
+    assert np.max(np.abs(got - ref)) < 2e-14 * np.max(np.abs(ref))
+    np.testing.assert_allclose(e.theta, g / g.sum(1, keepdims=True), rtol=1e-15)
+    np.testing.assert_array_equal(e.gamma, g)
+
+
+def test_first_snp_step(fixture_case):
+    """Minimum slice: SNP 4512, the first one sampled under seed 1234."""
+    c = fixture_case
+    s = make_driver(c)
+    o = ol.Oracle(c["y"], c["k"], c["seed"])
+    np.testing.assert_array_equal(s.val_loc, o.validation()[0])
+    np.testing.assert_array_equal(s.val_indiv, o.validation()[2])
+    np.testing.assert_array_equal(s.engine.gamma, o.gamma)
+    _, a0, cnt = o.heldout(first=True)
+    assert s.validation_rows[0][3] == cnt and abs(s.validation_rows[0][2] - a0) < 1e-12
+    loc = o.sample_loc()
+    assert loc == 4512
+    r_gpu = s.engine.step(loc)
+    r_cpu = o.train_loc(loc)
+    o.flush()
+    assert r_gpu == r_cpu
+    assert rel_err(s.engine.get_lambda(loc, 1)[0], o.lam[loc]) < 1e-13
+    assert rel_err(s.engine.gamma, o.gamma) < 1e-12
+    assert rel_err(s.engine.elogtheta, o.elogtheta) < 1e-11
+    np.testing.assert_array_equal(s.engine.counts, o.counts)
+
+
+def test_fixture_trajectory_to_stop(fixture_case):
+    """data/run.sh line 1 on the GPU: same reports and stop iteration as the reference binary,
+    LL within 1e-5, theta within 1e-6 relative of the reference's shipped output_theta.txt."""
+    c = fixture_case
+    g = c["gold"]
+    s = make_driver(c)
+    s.infer()
+    assert s.stopped and s._iter == 9050
+    it = [r[0] for r in s.validation_rows]
+    ll = np.array([r[2] for r in s.validation_rows])
+    assert it == g["val_iter"].tolist()
+    assert [r[3] for r in s.validation_rows] == g["val_count"].tolist()
+    assert np.max(np.abs(ll - g["val_ll"])) < LL_ATOL
+    assert np.max(np.abs(ll - g["val_ll"])) < 6e-10          # print precision of validation.txt
+    theta = s.engine.theta
+    # golden file holds 8 decimals: allow its half-ulp on top of the relative tolerance
+    assert np.all(np.abs(theta - g["shipped_theta"]) <= THETA_RTOL * np.abs(g["shipped_theta"]) + 5.1e-9)
+    assert np.max(np.abs(theta - g["shipped_theta"])) < 5.1e-9
+    assert np.max(np.abs(s.engine.gamma - g["gamma"])) < 5.1e-9 + 1e-9 * np.max(g["gamma"])
+
+
+@pytest.mark.parametrize("name", ["synthA", "synthB"])
+def test_synthetic_trajectory_vs_oracle_and_reference(name):
+    """Missing data, N<2000 and N>=2000 validation branches: every report of the reference
+    binary (golden) and the oracle's full-precision state at the last one."""
+    c = load_case(name)
+    g = c["gold"]
+    s = make_driver(c)
+    o = ol.Oracle(c["y"], c["k"], c["seed"])
+    o.heldout(first=True)
+    last = int(g["val_iter"][-1])
+    s.infer(max_iter=last)
+    o.infer(c["rfreq"], last)
+    it = [r[0] for r in s.validation_rows]
+    ll = np.array([r[2] for r in s.validation_rows])
+    assert it == g["val_iter"].tolist()
+    assert np.max(np.abs(ll - g["val_ll"])) < 6e-10
+    assert rel_err(s.engine.gamma, o.gamma) < TIGHT
+    assert rel_err(s.engine.theta, o.theta) < TIGHT
+    assert rel_err(s.engine.get_lambda(), o.lam) < TIGHT
+    np.testing.assert_array_equal(s.engine.counts, o.counts)
+    assert np.max(np.abs(s.engine.gamma - g[f"gamma_{last}"])) < 5.1e-9 + 1e-9 * np.max(o.gamma)
+
+
+def test_training_step_on_validation_locus(fixture_case):
+    """A training visit to a validation locus must skip the held-out individuals (kv_ok)."""
+    c = fixture_case
+    s = make_driver(c)
+    o = ol.Oracle(c["y"], c["k"], c["seed"])
+    locs = [int(s.val_loc[0]), 17, int(s.val_loc[3]), int(s.val_loc[0])]
+    rounds = s.engine.steps(np.array(locs, np.uint32), want_rounds=True)
+    ro = [o.train_loc(l) for l in locs]
+    o.flush()
+    assert rounds.tolist() == ro
+    assert rel_err(s.engine.gamma, o.gamma) < 1e-11
+    np.testing.assert_array_equal(s.engine.counts, o.counts)
+    held = s.val_indiv[s.val_off[0]:s.val_off[1]]
+    assert np.all(s.engine.counts[held] <= 2)  # never stepped on the two visits to val_loc[0]
+
+
+def test_heldout_per_locus(fixture_case):
+    c = fixture_case
+    s = make_driver(c)
+    o = ol.Oracle(c["y"], c["k"], c["seed"])
+    locs = [o.sample_loc() for _ in range(25)]
+    s.engine.steps(np.array(locs, np.uint32))
+    for l in locs:
+        o.train_loc(l)
+    ssum, cnt, per = s.engine.heldout_ll(False)
+    _, a, cnt_o, per_o = o.heldout(first=False, per_locus=True)
+    assert cnt == cnt_o == 1000
+    np.testing.assert_allclose(per, per_o, rtol=1e-11)
+    assert abs(ssum / cnt - a) < 1e-12
+    # hol-mode passes leave gamma alone but do overwrite lambda of the validation loci
+    assert rel_err(s.engine.gamma, o.gamma) < 1e-11
+    assert rel_err(s.engine.get_lambda(), o.lam) < 1e-11
+
+
+def test_compute_beta_pass(fixture_case):
+    """data/run.sh line 2 (-compute-beta): beta.txt of the reference binary (golden)."""
+    import terastructure_b200 as ts
+    c = fixture_case
+    g = c["gold"]
+    env = ts.Env(c["n"], c["k"], c["l"], seed=0, compute_beta=True)
+    s = ts.SNPSamplingE(env, c["rows"], gamma0=g["gamma"])
+    beta = s.compute_all_lambda()
+    assert np.all(np.abs(beta - g["beta"]) <= 1e-6 * np.abs(g["beta"]) + 5.1e-9)
+    assert np.max(np.abs(beta - g["beta"])) < 5.1e-9
+
+
+@pytest.mark.parametrize("k", [1, 2, 7, 13, 20, 32])
+def test_k_sweep_vs_oracle(k):
+    """K sweep (BASELINE configs[4]) at a size the oracle does in seconds."""
+    import terastructure_b200 as ts
+    from terastructure_b200 import plink, synth
+    n, l = 1501, 400   # ragged: N not a multiple of 4
+    y, _, _ = synth.psd_genotypes(n, l, max(k, 2), seed=3, missing_rate=0.03)
+    rows = plink.pack(y)
+    env = ts.Env(n, k, l, seed=21, rfreq=10 ** 6)
+    s = ts.SNPSamplingE(env, rows)
+    o = ol.Oracle(y, k, 21)
+    locs = [o.sample_loc() for _ in range(40)]
+    r = s.engine.steps(np.array(locs, np.uint32), want_rounds=True)
+    ro = [o.train_loc(x) for x in locs]
+    o.flush()
+    assert r.tolist() == ro
+    assert rel_err(s.engine.gamma, o.gamma) < TIGHT
+    assert rel_err(s.engine.get_lambda(), o.lam) < TIGHT
+
+
+def test_all_missing_column_and_tiny_n():
+    """Edge cases: a locus where every genotype is missing (lambda falls back to eta, no gamma
+    step), and N smaller than one warp."""
+    import terastructure_b200 as ts
+    from terastructure_b200 import plink
+    n, l, k = 13, 300, 3
+    rs = np.random.RandomState(5)
+    y = rs.randint(0, 3, size=(l, n)).astype(np.uint8)
+    y[7, :] = 3
+    rows = plink.pack(y)
+    env = ts.Env(n, k, l, seed=4, rfreq=10 ** 6)
+    s = ts.SNPSamplingE(env, rows)
+    o = ol.Oracle(y, k, 4)
+    locs = [5, 7, 7, 9, 7]
+    r = s.engine.steps(np.array(locs, np.uint32), want_rounds=True)
+    ro = [o.train_loc(x) for x in locs]
+    o.flush()
+    assert r.tolist() == ro
+    np.testing.assert_array_equal(s.engine.get_lambda(7, 1)[0], np.ones((k, 2)))
+    assert rel_err(s.engine.gamma, o.gamma) < TIGHT
+
+
+def test_invariants_at_scale():
+    """N=100K x L=64, K=10 generated on the device -- far beyond what the sequential oracle
+    does in seconds.  Size-independent checks:
+      sum_k lambda[loc][k][0] - K*eta0 = sum_n y[n]       over non-missing n (phi sums to one)
+      sum_k lambda[loc][k][1] - K*eta1 = sum_n (2 - y[n])
+      rowsum(gamma) follows  s <- (1-rho) s + rho (K*alpha + 2L)  per visit,  rho = (2+c)^-0.5
+      counts[n] = number of visits with a non-missing genotype."""
+    import terastructure_b200 as ts
+    from terastructure_b200 import plink, synth
+    n, l, k = 100_000, 64, 10
+    theta, beta = synth.psd_params(n, l, k, seed=1)
+    e = ts.Engine(n, l, k)
+    e.synth_bed(99, theta, beta, missing_rate=0.01)
+    rs = np.random.RandomState(2)
+    g0 = rs.gamma(100.0, 0.01, size=(n, k))
+    e.set_gamma(g0)
+    locs = rs.randint(0, l, size=30).astype(np.uint32)
+    rounds = e.steps(locs, want_rounds=True)
+    assert np.all(rounds == 10)  # at N>=10K every visit runs all 10 rounds
+    rowsum = g0.sum(1)
+    cnt = np.zeros(n, np.int64)
+    last_visit = {}
+    for i, loc in enumerate(locs):
+        y = plink.unpack(e.get_bed_row(int(loc))[None, :], n)[0]
+        ok = y != 3
+        rho = (2.0 + cnt) ** -0.5
+        rowsum = np.where(ok, (1 - rho) * rowsum + rho * (k * (1.0 / k) + 2.0 * l), rowsum)
+        cnt += ok
+        last_visit[int(loc)] = y
+    np.testing.assert_array_equal(e.counts, cnt)
+    np.testing.assert_allclose(e.gamma.sum(1), rowsum, rtol=1e-12)
+    for loc, y in last_visit.items():
+        lam = e.get_lambda(loc, 1)[0]
+        ok = y != 3
+        assert abs(lam[:, 0].sum() - k - y[ok].sum()) < 1e-7 * n
+        assert abs(lam[:, 1].sum() - k - (2 - y[ok].astype(np.int64)).sum()) < 1e-7 * n
+    # generator sanity: allele frequency tracks theta.beta
+    y0 = plink.unpack(e.get_bed_row(0)[None, :], n)[0]
+    q = theta @ beta[0]
+    assert abs(y0[y0 != 3].mean() / 2 - q.mean()) < 0.01
+    assert abs((y0 == 3).mean() - 0.01) < 0.003
+
+
+def test_two_shards_match_one(fixture_case):
+    """Individuals sharded over two engines (here: both on cuda:0, exchange through the same
+    peer-store protocol used across NVLink) give the single-engine result."""
+    import terastructure_b200 as ts
+    from terastructure_b200 import capi
+    c = load_case("synthA")
+    n, l, k = c["n"], c["l"], c["k"]
+    r = ts.Rng(c["seed"])
+    vl, vo, vi = r.sample_validation(n, l, c["rows"])
+    g0 = r.init_gamma(n, k)
+    locs = r.sample_locs(l, 50)
+    locs[10] = vl[0]
+    one = ts.Engine(n, l, k)
+    one.load_bed(c["rows"]); one.set_validation(vl, vo, vi); one.set_gamma(g0)
+    half = 300
+    sh = [ts.Engine(n, l, k, rank=i, nranks=2, n_begin=i * half, n_local=half) for i in range(2)]
+    for i, e in enumerate(sh):
+        e.load_bed(c["rows"]); e.set_validation(vl, vo, vi); e.set_gamma(g0[i * half:(i + 1) * half])
+    capi.connect_local(sh)
+    one.steps(locs)
+    # interleave the two shards SNP by SNP so neither stream waits long for its peer
+    for x in locs:
+        for e in sh:
+            e.steps(np.array([x], np.uint32))
+    s1, c1, p1 = one.heldout_ll(False)
+    per = np.zeros(len(vl)); cnt = 0
+    import threading
+    res = [None, None]
+    th = [threading.Thread(target=lambda i=i: res.__setitem__(i, sh[i].heldout_ll(False))) for i in range(2)]
+    [t.start() for t in th]; [t.join() for t in th]
+    for sres in res:
+        per += sres[2]; cnt += sres[1]
+    assert cnt == c1
+    np.testing.assert_allclose(per, p1, rtol=1e-10)
+    gs = np.concatenate([e.gamma for e in sh])
+    assert rel_err(gs, one.gamma) < 1e-11
+    np.testing.assert_array_equal(sh[0].get_lambda(), sh[1].get_lambda())  # bit-identical on all ranks
+    assert rel_err(sh[0].get_lambda(), one.get_lambda()) < 1e-11

@@ -1,0 +1,126 @@
+"""CPU tests of the product's host side: the C ABI library loads and exports every symbol
+include/tsgpu.h declares, the GSL-exact host RNG / validation sampler / init_gamma agree with
+the oracle and the golden vectors, the packed-genotype helpers round-trip, and compute entry
+points fail loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from conftest import ROOT, load_case
+
+
+def test_cabi_exports_match_header():
+    import terastructure_b200 as ts
+    from terastructure_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "tsgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ts_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = C.CDLL(ts.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in tsgpu.h but not exported"
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+    assert ts.lib().ts_abi_version() == 1
+
+
+def test_mt19937_known_answer():
+    """MT19937 seeded with 4357 (GSL's default seed): 10000th output, and seed 5489's first."""
+    import terastructure_b200 as ts
+    r = ts.Rng(0)
+    rs = np.random.RandomState(4357)
+    ref = rs.randint(0, 2 ** 32, size=1000, dtype=np.uint64)
+    got = [r.get() for _ in range(1000)]
+    assert got == ref.tolist()
+    r = ts.Rng(5489)
+    assert r.get() == 3499211612  # reference value of the MT19937 paper's init_genrand(5489)
+
+
+def test_host_init_matches_oracle_and_golden(fixture_case):
+    import terastructure_b200 as ts
+    c = fixture_case
+    r = ts.Rng(c["seed"])
+    vl, vo, vi = r.sample_validation(c["n"], c["l"], c["rows"])
+    g0 = r.init_gamma(c["n"], c["k"])
+    locs = r.sample_locs(c["l"], 2000)
+    o = ol.Oracle(c["y"], c["k"], c["seed"])
+    ovl, ovo, ovi = o.validation()
+    np.testing.assert_array_equal(vl, ovl)
+    np.testing.assert_array_equal(vo, ovo)
+    np.testing.assert_array_equal(vi, ovi)
+    np.testing.assert_array_equal(g0, o.gamma)
+    assert locs.tolist() == [o.sample_loc() for _ in range(2000)]
+    assert locs[:12].tolist() == [4512, 5810, 6508, 3177, 8093, 7291, 2829, 6486, 2733, 7778, 3857, 648]
+
+
+@pytest.mark.parametrize("name", ["synthA", "synthB"])
+def test_host_init_synthetic(name):
+    """Missing genotypes are rejected by the sampler (kv_ok); N>=2000 uses N/100 per locus."""
+    import terastructure_b200 as ts
+    c = load_case(name)
+    r = ts.Rng(c["seed"])
+    vl, vo, vi = r.sample_validation(c["n"], c["l"], c["rows"])
+    g0 = r.init_gamma(c["n"], c["k"])
+    o = ol.Oracle(c["y"], c["k"], c["seed"])
+    ovl, ovo, ovi = o.validation()
+    np.testing.assert_array_equal(vl, ovl)
+    np.testing.assert_array_equal(vi, ovi)
+    np.testing.assert_array_equal(g0, o.gamma)
+    np.testing.assert_allclose(g0, c["gold"]["gamma_0"], atol=5.1e-9)
+    per = c["n"] // 10 if c["n"] < 2000 else c["n"] // 100
+    assert np.all(np.diff(vo) == per)
+    for j in range(len(vl)):
+        assert np.all(c["y"][vl[j], vi[vo[j]:vo[j + 1]]] != 3)
+
+
+def test_plink_roundtrip_and_codes():
+    from terastructure_b200 import plink
+    rs = np.random.RandomState(1)
+    for n in (1, 3, 4, 5, 203):
+        y = rs.randint(0, 4, size=(17, n)).astype(np.uint8)
+        rows = plink.pack(y)
+        assert rows.shape == (17, (n + 3) // 4)
+        np.testing.assert_array_equal(plink.unpack(rows, n), y)
+        np.testing.assert_array_equal(ol.decode_bed(rows.tobytes(), n, 17), y)
+    # snp.cc:203-216: 00->0, 01->missing, 10->1, 11->2 (low bits first)
+    assert plink.unpack(np.array([[0b11100100]], np.uint8), 4).tolist() == [[0, 3, 1, 2]]
+
+
+def test_read_bed_checks(tmp_path):
+    from terastructure_b200 import plink
+    y = np.random.RandomState(0).randint(0, 3, size=(6, 9)).astype(np.uint8)
+    bed = plink.write_bed(str(tmp_path / "t"), plink.pack(y), 9)
+    np.testing.assert_array_equal(plink.unpack(plink.read_bed(bed, 9, 6), 9), y)
+    with pytest.raises(ValueError, match="-l input"):
+        plink.read_bed(bed, 9, 7)
+    with pytest.raises(ValueError, match="-n input"):
+        plink.read_bed(bed, 8, 6)
+    raw = bytearray(open(bed, "rb").read()); raw[2] = 0
+    open(bed, "wb").write(raw)
+    with pytest.raises(ValueError, match="individual major"):
+        plink.read_bed(bed, 9, 6)
+
+
+def test_compute_fails_loudly_without_gpu():
+    import terastructure_b200 as ts
+    if ts.lib().ts_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(ts.TsError, match="no CUDA device"):
+        ts.Engine(16, 4, 2)
+
+
+def test_argument_validation():
+    import terastructure_b200 as ts
+    from terastructure_b200 import capi
+    cfg = capi.TsConfig()
+    ts.lib().ts_config_defaults(C.byref(cfg), 100, 10, 3)
+    assert (cfg.alpha, cfg.eta0, cfg.nodetau0, cfg.nodekappa, cfg.online_iterations) == (1 / 3, 1.0, 2.0, 0.5, 10)
+    h = C.c_void_p()
+    cfg.k = 33
+    assert ts.lib().ts_create(C.byref(cfg), C.byref(h)) == -1 and b"K=33" in ts.lib().ts_last_error()
+    cfg.k = 3; cfg.n_begin = 2
+    assert ts.lib().ts_create(C.byref(cfg), C.byref(h)) == -1
+    assert ts.lib().ts_steps(None, None, 0, 0, None) == -1
