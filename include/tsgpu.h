@@ -183,7 +183,8 @@ double ts_rng_gamma(ts_rng *r, double a, double b);   /* gsl_ran_gamma (cc:233) 
 void ts_rng_sample_locs(ts_rng *r, uint32_t l, uint32_t *out, uint64_t n);
 
 /* set_validation_sample (snpsamplinge.cc:196-224) with identical draw and rejection order.
- * `bed` = whole-data-set SNP-major rows (for the is_missing test).  Outputs are malloc'ed
+ * `bed` = whole-data-set SNP-major rows (for the is_missing test), or NULL when the data set
+ * has no missing genotypes (device-generated synthetic data).  Outputs are malloc'ed
  * CSR arrays in ascending locus order, released with ts_free. */
 int ts_sample_validation(ts_rng *r, uint64_t n, uint64_t l, const uint8_t *bed, uint64_t row_pitch,
                          uint64_t *nval_out, uint32_t **val_loc_out, uint64_t **val_off_out,

@@ -129,11 +129,15 @@ class Rng:
 
     def sample_validation(self, n, l, bed_rows):
         """set_validation_sample (snpsamplinge.cc:196-224) -> CSR (val_loc, val_off, val_indiv)."""
-        bed_rows = np.ascontiguousarray(bed_rows, dtype=np.uint8)
-        assert bed_rows.ndim == 2 and bed_rows.shape[0] == l and bed_rows.shape[1] >= (n + 3) // 4
+        if bed_rows is None:  # no missing genotypes anywhere (device-generated synthetic data)
+            bed_ptr, pitch = None, 0
+        else:
+            bed_rows = np.ascontiguousarray(bed_rows, dtype=np.uint8)
+            assert bed_rows.ndim == 2 and bed_rows.shape[0] == l and bed_rows.shape[1] >= (n + 3) // 4
+            bed_ptr, pitch = bed_rows.ctypes.data, bed_rows.shape[1]
         nval = _u64()
         pl, po, pi = _vp(), _vp(), _vp()
-        check(lib().ts_sample_validation(self._h, n, l, bed_rows.ctypes.data, bed_rows.shape[1],
+        check(lib().ts_sample_validation(self._h, n, l, bed_ptr, pitch,
                                          C.byref(nval), C.byref(pl), C.byref(po), C.byref(pi)))
         nv = nval.value
         loc = np.ctypeslib.as_array(C.cast(pl, C.POINTER(_u32)), (max(nv, 1),))[:nv].copy()

@@ -128,7 +128,7 @@ void ts_init_gamma(ts_rng *r, uint64_t n, uint32_t k, double *gamma_out) {
 int ts_sample_validation(ts_rng *r, uint64_t n, uint64_t l, const uint8_t *bed, uint64_t row_pitch,
                          uint64_t *nval_out, uint32_t **val_loc_out, uint64_t **val_off_out,
                          uint32_t **val_indiv_out) {
-  if (!r || !bed || n == 0 || l == 0 || n > 0xffffffffull || l > 0xffffffffull) return TS_ERR_ARG;
+  if (!r || n == 0 || l == 0 || n > 0xffffffffull || l > 0xffffffffull) return TS_ERR_ARG;
   const uint32_t per_loc_h = (uint32_t)(n < 2000 ? n / 10 : n / 100);
   const uint64_t nlocs = (uint64_t)(l * 0.005);
   std::vector<uint8_t> taken(l, 0);
@@ -142,12 +142,12 @@ int ts_sample_validation(ts_rng *r, uint64_t n, uint64_t l, const uint8_t *bed, 
     drawn.push_back(loc);
     masks.emplace_back(words, 0ull);
     std::vector<uint64_t> &m = masks.back();
-    const uint8_t *row = bed + (size_t)loc * row_pitch;
+    const uint8_t *row = bed ? bed + (size_t)loc * row_pitch : nullptr;
     uint32_t c = 0;
     while (c < per_loc_h) {
       const uint32_t indiv = r->uniform_int((uint32_t)n);
       const bool held = (m[indiv >> 6] >> (indiv & 63)) & 1ull;
-      const bool missing = ((row[indiv >> 2] >> (2 * (indiv & 3))) & 3) == 1;
+      const bool missing = row && ((row[indiv >> 2] >> (2 * (indiv & 3))) & 3) == 1;
       if (!held && !missing) {  // kv_ok (snpsamplinge.hh:389-408)
         m[indiv >> 6] |= 1ull << (indiv & 63);
         c++;
