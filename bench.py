@@ -129,6 +129,8 @@ def run_reference_cpu(n, k, steps, warmup, budget_s=150.0):
             now = time.time()
             if chunk:
                 buf += chunk
+                if b"initialization end" in buf:      # ctor done (snpsamplinge.cc:112): infer() starts
+                    stamps.setdefault(0, now)
                 for m in re.finditer(rb"iteration = (\d+) took", buf):
                     stamps.setdefault(int(m.group(1)), now)
                 buf = buf[-64:]
@@ -136,7 +138,7 @@ def run_reference_cpu(n, k, steps, warmup, budget_s=150.0):
                 time.sleep(0.01)
             done = [i for i in stamps if i >= want_last]
             first_timed = warmup * REF_STEP_ITERS
-            have = sorted(i for i in stamps if i >= max(first_timed, REF_STEP_ITERS))
+            have = sorted(i for i in stamps if i >= first_timed)
             if done or (now - t_start > budget_s and len(have) >= 2) or now - t_start > 3 * budget_s:
                 break
     finally:
@@ -203,12 +205,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--individuals", type=int, default=0, help="override individuals per GPU (debug)")
     ap.add_argument("--snps", type=int, default=0, help="override L (debug)")
+    ap.add_argument("--batch", type=int, default=0, help="override SVI iterations per step (debug/profiling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
     if args.warmup < 3:
         args.warmup = 3
+    global BATCH
+    if args.batch:
+        BATCH = args.batch
 
     import torch
     import torch.distributed as dist
@@ -303,7 +309,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world) if not (args.individuals or args.snps) else
+            "config": workload_config(world) if not (args.individuals or args.snps or args.batch) else
             {"workload": f"DEBUG override: {n_total} x {l}, K={K}", "svi_iterations_per_step": BATCH},
             "clocks": clocks,
             "e2e": {"value": genos / e2e_s, "unit": UNIT, "h2d_bytes_per_step": BATCH * 24,

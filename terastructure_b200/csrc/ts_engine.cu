@@ -89,6 +89,22 @@ struct Xbuf {
   unsigned long long flag[2][MAXR];
 };
 
+// State of the persistent kernel's fence-free grid barrier (ts_persist.cuh).
+struct PState {
+  unsigned long long acc[2][2][2 * MAXK];         // [round parity][hi/lo word][statistic], monotonic
+  unsigned long long prev[2][2][2 * MAXK];        // totals at the end of the previous launch
+  unsigned long long slot[MAXR][2][2][2 * MAXK];  // [source rank][parity][hi/lo][statistic], peer-written
+  unsigned long long round_ctr;                   // rounds run so far (slot tags; same on every rank)
+  uint32_t fault;
+  uint32_t pad;
+};
+
+// Everything a peer GPU writes into lives in one allocation (one IPC handle).
+struct Xchg {
+  Xbuf x;
+  PState ps;
+};
+
 struct Params {
   const unsigned char *bed;
   size_t pitch;
@@ -113,6 +129,10 @@ struct Params {
   int rank, nranks;
   Xbuf *xlocal;
   Xbuf *xpeer[MAXR];
+  // persistent kernel
+  PState *pst;
+  PState *pst_peer[MAXR];
+  double fx_scale, fx_inv;  // 2^sh and 2^-sh of the fixed-point statistics
 };
 
 // ------------------------------------------------------------------------------------------
@@ -348,12 +368,13 @@ __global__ void __launch_bounds__(256) k_gamma(Params p) {
   }
 }
 
-// snp_likelihood (hh:322-361) for the validation locus of the current item: one CTA.
+// snp_likelihood (hh:322-361): one CTA per work item (= validation locus).  gamma does not
+// change during a held-out pass and every locus owns its lambda row, so the whole pass is
+// scored by one launch after the hol-mode optimisations.
 template <int K>
 __global__ void __launch_bounds__(256) k_heldout(Params p) {
-  const Ctl *c = p.ctl;
-  const WorkItem it = p.items[c->cursor];
-  if (it.vslot < 0) return;
+  const WorkItem it = p.items[blockIdx.x];
+  if (it.vslot < 0 || !(it.flags & ITEM_HOL)) return;
   const unsigned char *col = p.bed + (size_t)it.loc * p.pitch;  // the unmasked column
   double beta[K];
 #pragma unroll
@@ -490,6 +511,8 @@ __global__ void k_synth(unsigned char *bed, size_t pitch, uint64_t L, uint32_t n
   }
 }
 
+#include "ts_persist.cuh"
+
 // ------------------------------------------------------------------------------------------
 // host-side engine
 // ------------------------------------------------------------------------------------------
@@ -506,7 +529,10 @@ struct ts_engine {
   Ctl *ctl = nullptr;
   WorkItem *items = nullptr;
   size_t items_cap = 0;
-  Xbuf *xbuf = nullptr;
+  Xchg *xchg = nullptr;
+  Xbuf *xbuf = nullptr;  // &xchg->x
+  bool staged = false;   // TSGPU_PATH=staged: one launch per round (debug cross-check path)
+  int grid_persist = 1, block_persist = 32;
   std::vector<void *> ipc_opened;
   // validation set (host copies)
   std::vector<uint32_t> val_loc;         // ascending
@@ -560,6 +586,7 @@ static void fill_params(ts_engine *e) {
   p.rank = e->cfg.rank;
   p.nranks = e->cfg.nranks;
   p.xlocal = e->xbuf;
+  p.pst = &e->xchg->ps;
 }
 
 // K dispatch ---------------------------------------------------------------------------------
@@ -583,13 +610,39 @@ static void launch_gamma(ts_engine *e) {
 #undef X
   }
 }
-static void launch_heldout(ts_engine *e) {
+static void launch_heldout(ts_engine *e, unsigned n_items) {
   switch (e->K) {
 #define X(k) \
-  case k: k_heldout<k><<<1, 256, 0, e->stream>>>(e->prm); break;
+  case k: k_heldout<k><<<n_items, 256, 0, e->stream>>>(e->prm); break;
     TS_FOR_EACH_K(X)
 #undef X
   }
+}
+
+// persistent-kernel launch (cooperative: every CTA must be resident for the grid barrier)
+template <int K>
+static cudaError_t launch_persist_k(ts_engine *e, uint32_t n_items) {
+  void *args[] = {(void *)&e->prm, (void *)&n_items};
+  return cudaLaunchCooperativeKernel((const void *)tsp::k_persist<K>, dim3(e->grid_persist),
+                                     dim3(e->block_persist), args, 0, e->stream);
+}
+static cudaError_t launch_persist(ts_engine *e, uint32_t n_items) {
+  switch (e->K) {
+#define X(k) \
+  case k: return launch_persist_k<k>(e, n_items);
+    TS_FOR_EACH_K(X)
+#undef X
+  }
+  return cudaErrorInvalidValue;
+}
+static int persist_tmax(int K) {
+  switch (K) {
+#define X(k) \
+  case k: return tsp::Cfg<k>::TMAX;
+    TS_FOR_EACH_K(X)
+#undef X
+  }
+  return 256;
 }
 
 extern "C" {
@@ -677,16 +730,35 @@ int ts_create(const ts_config *cfg, ts_engine **out) {
   CKE(dalloc(&e->cnt, e->npad));
   CKE(dalloc(&e->lambda, (size_t)cfg->l * K * 2));
   CKE(dalloc(&e->ctl, 1));
-  CKE(dalloc(&e->xbuf, 1));
+  CKE(dalloc(&e->xchg, 1));
+  e->xbuf = &e->xchg->x;
   CKE(cudaMemsetAsync(e->gamma, 0, K * e->npad * sizeof(double), e->stream));
   CKE(cudaMemsetAsync(e->E, 0, K * e->npad * sizeof(double), e->stream));
   CKE(cudaMemsetAsync(e->cnt, 0, e->npad * sizeof(uint32_t), e->stream));
   CKE(cudaMemsetAsync(e->ctl, 0, sizeof(Ctl), e->stream));
-  CKE(cudaMemsetAsync(e->xbuf, 0, sizeof(Xbuf), e->stream));
+  CKE(cudaMemsetAsync(e->xchg, 0, sizeof(Xchg), e->stream));
   // Grid sizing: whole CTAs of individuals, capped at two CTAs per SM.
   const int need = (int)((cfg->n_local + ESTEP_THREADS - 1) / ESTEP_THREADS);
   e->grid_estep = std::max(1, std::min(need, e->num_sms));
   e->grid_gamma = std::max(1, std::min(need, 4 * e->num_sms));
+  {
+    // Persistent kernel: one CTA per SM at most, threads sized so that every thread owns the
+    // same number of individuals (I = ceil(n / (SMs * TMAX))).
+    const char *path = getenv("TSGPU_PATH");
+    e->staged = path && !strcmp(path, "staged");
+    const int tmax = persist_tmax(e->K);
+    const uint64_t n = cfg->n_local;
+    const uint64_t per_thread = (n + (uint64_t)e->num_sms * tmax - 1) / ((uint64_t)e->num_sms * tmax);
+    const uint64_t threads = (n + per_thread - 1) / per_thread;
+    e->grid_persist = (int)std::min<uint64_t>(e->num_sms, (threads + tmax - 1) / tmax);
+    const uint64_t t = (threads + e->grid_persist - 1) / e->grid_persist;
+    e->block_persist = (int)std::min<uint64_t>(tmax, (t + 31) / 32 * 32);
+    int bits = 1;
+    while ((2 * cfg->n_total + 2) >> bits) bits++;
+    const int sh = 53 - bits;
+    e->prm.fx_scale = ldexp(1.0, sh);
+    e->prm.fx_inv = ldexp(1.0, -sh);
+  }
   CKE(dalloc(&e->partial, (size_t)e->grid_estep * 2 * K));
   e->items_cap = 1 << 16;
   CKE(dalloc(&e->items, e->items_cap));
@@ -694,7 +766,10 @@ int ts_create(const ts_config *cfg, ts_engine **out) {
   CKE(dalloc(&e->ll, 1));
 #undef CKE
   fill_params(e);
-  for (int r = 0; r < MAXR; ++r) e->prm.xpeer[r] = e->xbuf;
+  for (int r = 0; r < MAXR; ++r) {
+    e->prm.xpeer[r] = e->xbuf;
+    e->prm.pst_peer[r] = &e->xchg->ps;
+  }
   const size_t cnt = (size_t)cfg->l * K * 2;
   k_fill_lambda<<<std::min<size_t>((cnt + 255) / 256, 4096), 256, 0, e->stream>>>(e->lambda, cnt, cfg->eta0, cfg->eta1);
   e->launches++;
@@ -719,7 +794,7 @@ int ts_destroy(ts_engine *e) {
   cudaFree(e->rounds);
   cudaFree(e->ctl);
   cudaFree(e->items);
-  cudaFree(e->xbuf);
+  cudaFree(e->xchg);
   cudaFree(e->d_voff);
   cudaFree(e->d_vind);
   cudaFree(e->d_val_loc);
@@ -857,33 +932,54 @@ int ts_reset_counts(ts_engine *e) {
 }
 
 // Enqueue a batch of work items (<= items_cap) and the kernels that process them.
+static int check_fault(ts_engine *e) {
+  uint32_t fault[2] = {0, 0};
+  CK(cudaMemcpy(&fault[0], &e->ctl->fault, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&fault[1], &e->xchg->ps.fault, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (fault[0] || fault[1])
+    return set_err(TS_ERR_CUDA, "grid/peer barrier timed out (a CTA or a rank stopped responding)");
+  return TS_OK;
+}
+
+// Enqueue a batch of work items (<= items_cap) and the kernels that process them.
 static int run_items(ts_engine *e, const std::vector<WorkItem> &items, uint32_t *rounds_out) {
   const size_t n = items.size();
   if (n == 0) return TS_OK;
   // The previous batch may still be reading items[]: drain before overwriting.
   CK(cudaStreamSynchronize(e->stream));
   CK(cudaMemcpyAsync(e->items, items.data(), n * sizeof(WorkItem), cudaMemcpyHostToDevice, e->stream));
-  const long long minus1 = -1;
-  CK(cudaMemcpyAsync(&e->ctl->cursor, &minus1, sizeof(long long), cudaMemcpyHostToDevice, e->stream));
-  for (size_t i = 0; i < n; ++i) {
-    k_begin<<<1, 32, 0, e->stream>>>(e->prm, e->K);
+  const bool first = (items[0].flags & ITEM_FIRST) != 0;  // a batch is all-first or none
+  const bool hol = (items[0].flags & ITEM_HOL) != 0;      // and all-hol or none
+  if (first) {
+    CK(cudaMemsetAsync(e->rounds, 0, n * sizeof(uint32_t), e->stream));
+  } else if (!e->staged) {
+    CK(launch_persist(e, (uint32_t)n));
     e->launches++;
-    if (!(items[i].flags & ITEM_FIRST))
+  } else {
+    const long long minus1 = -1;
+    CK(cudaMemcpyAsync(&e->ctl->cursor, &minus1, sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+    for (size_t i = 0; i < n; ++i) {
+      k_begin<<<1, 32, 0, e->stream>>>(e->prm, e->K);
+      e->launches++;
       for (uint32_t x = 0; x < e->cfg.online_iterations; ++x) {
         launch_estep(e);
         e->launches++;
       }
-    if (items[i].flags & ITEM_HOL) launch_heldout(e);
-    else launch_gamma(e);
+      if (!hol) {
+        launch_gamma(e);
+        e->launches++;
+      }
+    }
+  }
+  if (hol) {
+    launch_heldout(e, (unsigned)n);
     e->launches++;
   }
   CK(cudaGetLastError());
   if (rounds_out) {
     CK(cudaMemcpyAsync(rounds_out, e->rounds, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    uint32_t fault = 0;
-    CK(cudaMemcpy(&fault, &e->ctl->fault, sizeof fault, cudaMemcpyDeviceToHost));
-    if (fault) return set_err(TS_ERR_CUDA, "peer exchange timed out (a rank stopped responding)");
+    return check_fault(e);
   }
   return TS_OK;
 }
@@ -943,9 +1039,7 @@ int ts_heldout_ll(ts_engine *e, int first, double *sum, uint64_t *count, double 
   }
   if (nval) CK(cudaMemcpyAsync(ll.data(), e->ll, nval * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  uint32_t fault = 0;
-  CK(cudaMemcpy(&fault, &e->ctl->fault, sizeof fault, cudaMemcpyDeviceToHost));
-  if (fault) return set_err(TS_ERR_CUDA, "peer exchange timed out (a rank stopped responding)");
+  if (int rc = check_fault(e)) return rc;
   double s = 0.0;
   for (size_t v = 0; v < nval; ++v) s += ll[v];
   if (per_locus_sum) memcpy(per_locus_sum, ll.data(), nval * sizeof(double));
@@ -1027,7 +1121,7 @@ int ts_comm_export(ts_engine *e, void *handle_out) {
   if (use_device(e)) return TS_ERR_CUDA;
   static_assert(sizeof(cudaIpcMemHandle_t) == TS_COMM_HANDLE_BYTES, "IPC handle size");
   cudaIpcMemHandle_t h;
-  CK(cudaIpcGetMemHandle(&h, e->xbuf));
+  CK(cudaIpcGetMemHandle(&h, e->xchg));
   memcpy(handle_out, &h, sizeof h);
   return TS_OK;
 }
@@ -1039,6 +1133,7 @@ int ts_comm_connect(ts_engine *e, const void *all_handles) {
   for (int r = 0; r < e->cfg.nranks; ++r) {
     if (r == e->cfg.rank) {
       e->prm.xpeer[r] = e->xbuf;
+      e->prm.pst_peer[r] = &e->xchg->ps;
       continue;
     }
     cudaIpcMemHandle_t h;
@@ -1046,7 +1141,8 @@ int ts_comm_connect(ts_engine *e, const void *all_handles) {
     void *p = nullptr;
     CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     e->ipc_opened.push_back(p);
-    e->prm.xpeer[r] = (Xbuf *)p;
+    e->prm.xpeer[r] = &((Xchg *)p)->x;
+    e->prm.pst_peer[r] = &((Xchg *)p)->ps;
   }
   return TS_OK;
 }
@@ -1069,6 +1165,7 @@ int ts_comm_connect_local(ts_engine **engines, int n) {
         cudaGetLastError();
       }
       e->prm.xpeer[j] = engines[j]->xbuf;
+      e->prm.pst_peer[j] = &engines[j]->xchg->ps;
     }
   }
   return TS_OK;
