@@ -318,7 +318,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "SVI iteration pipeline (k_begin + k_estep x10 + k_gamma per SNP)",
+                         "kernel": "tsp::k_persist<10> (one cooperative launch per step = BATCH SVI iterations)",
                          "algorithmic_bytes_per_genotype": bpg},
             "wall_s_timed_region": t_wall, "mean_rounds_per_snp": rounds_total / (BATCH * args.steps),
             "us_per_svi_iteration": 1e3 * dev_ms / (BATCH * args.steps),

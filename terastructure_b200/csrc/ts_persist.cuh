@@ -109,11 +109,17 @@ __global__ void __launch_bounds__(Cfg<K>::TMAX, 1) k_persist(Params p, uint32_t 
   const unsigned long long G = gridDim.x;
 
   // which statistic this lane ends up holding after tr_reduce
+  // (tr_level splits a NOMINAL count that is the same for every lane; a lane that took a short
+  // upper half carries zero padding, so its live count can be smaller than the nominal one)
   int tr_start = 0, tr_len = V;
+  {
+    int nominal = V;
 #pragma unroll
-  for (int bit = 16; bit > 0; bit >>= 1) {
-    const int lo = (tr_len + 1) / 2;
-    if (lane & bit) { tr_start += lo; tr_len -= lo; } else tr_len = lo;
+    for (int bit = 16; bit > 0; bit >>= 1) {
+      const int lo = (nominal + 1) / 2;
+      if (lane & bit) { tr_start += lo; tr_len = max(tr_len - lo, 0); } else tr_len = min(tr_len, lo);
+      nominal = lo;
+    }
   }
 
   // control-warp state: previous totals of the two accumulator sets, current lambda row
@@ -174,9 +180,10 @@ __global__ void __launch_bounds__(Cfg<K>::TMAX, 1) k_persist(Params p, uint32_t 
 #pragma unroll
       for (int v = 0; v < V; ++v) vv[v] = 0.0;
       for (uint32_t n = gtid; n < p.n_local; n += GT) {
+        // missing or held out (kv_ok, hh:389-408) -> weight 0; branch-free so the warp stays converged
         const int code = tsm::plink_code(col, n);
-        if (code == 1) continue;  // missing or held out (kv_ok, hh:389-408)
         const int y = tsm::code_to_y(code);
+        const double w0 = (code == 1) ? 0.0 : (double)y, w1 = (code == 1) ? 0.0 : (double)(2 - y);
         double e[K], s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -184,7 +191,7 @@ __global__ void __launch_bounds__(Cfg<K>::TMAX, 1) k_persist(Params p, uint32_t 
           s0 = fma(e[k], s_bcur[2 * k], s0);
           s1 = fma(e[k], s_bcur[2 * k + 1], s1);
         }
-        const double r0 = (double)y * fast_rcp(s0), r1 = (double)(2 - y) * fast_rcp(s1);
+        const double r0 = w0 * fast_rcp(s0), r1 = w1 * fast_rcp(s1);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           vv[2 * k] = fma(e[k], r0, vv[2 * k]);
@@ -192,6 +199,10 @@ __global__ void __launch_bounds__(Cfg<K>::TMAX, 1) k_persist(Params p, uint32_t 
         }
       }
       // ---- warp: transposed reduction; CTA: one warp per statistic --------------------------
+      // The loop above has a lane-dependent trip count; reconverge the warp explicitly before the
+      // shuffles (shfl.sync requires every named lane to execute the SAME instruction, and the
+      // compiler is free to duplicate the loop tail).
+      __syncwarp();
       tr_reduce<V>(vv, lane);
 #pragma unroll
       for (int q = 0; q < VPL; ++q)
