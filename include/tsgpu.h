@@ -168,6 +168,9 @@ uint64_t ts_launch_count(const ts_engine *e);
  * engine's stream.  ts_timer_start records, ts_timer_stop records + syncs, returns ms. */
 int ts_timer_start(ts_engine *e);
 int ts_timer_stop(ts_engine *e, float *ms_out);
+/* Developer aid: with TSGPU_TRACE=1 in the environment at ts_create, CTA 0 of the persistent kernel
+ * stamps clock64() at its phase boundaries for the first 64 work items of a launch (64 x 128 slots). */
+int ts_debug_trace(ts_engine *e, long long *out);
 
 /* ---- host-side, RNG-exact initialisation (no GPU needed) ------------------------------
  * The SNP-sampling RNG stays on the host and must reproduce the reference's GSL stream

@@ -62,6 +62,7 @@ EXPORTS = {
     "ts_launch_count": (_u64, [_vp]),
     "ts_timer_start": (_i, [_vp]),
     "ts_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
+    "ts_debug_trace": (_i, [_vp, _vp]),
     "ts_rng_create": (_vp, [_d]),
     "ts_rng_destroy": (None, [_vp]),
     "ts_rng_get": (_u32, [_vp]),
@@ -277,6 +278,11 @@ class Engine:
     @property
     def launch_count(self):
         return lib().ts_launch_count(self._h)
+
+    def debug_trace(self):
+        out = np.zeros((64, 128), dtype=np.int64)
+        check(lib().ts_debug_trace(self._h, out.ctypes.data))
+        return out
 
     def timer_start(self):
         check(lib().ts_timer_start(self._h))

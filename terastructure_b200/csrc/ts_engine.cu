@@ -91,10 +91,12 @@ struct Xbuf {
 
 // State of the persistent kernel's fence-free grid barrier (ts_persist.cuh).
 struct PState {
-  unsigned long long acc[2][2][2 * MAXK];         // [round parity][hi/lo word][statistic], monotonic
-  unsigned long long prev[2][2][2 * MAXK];        // totals at the end of the previous launch
-  unsigned long long slot[MAXR][2][2][2 * MAXK];  // [source rank][parity][hi/lo][statistic], peer-written
-  unsigned long long round_ctr;                   // rounds run so far (slot tags; same on every rank)
+  // [round parity][word = (hi|lo) * 2K + statistic][0]: monotonic fixed-point accumulators, one per
+  // 1 KB so that the 4K words of a round spread over the L2 slices
+  unsigned long long acc[2][4 * MAXK][128];
+  unsigned long long prev[2][4 * MAXK];        // totals at the end of the previous launch
+  unsigned long long slot[MAXR][2][4 * MAXK];  // [source rank][parity][word], peer-written
+  unsigned long long round_ctr;                // rounds run so far (slot tags; same on every rank)
   uint32_t fault;
   uint32_t pad;
 };
@@ -133,6 +135,7 @@ struct Params {
   PState *pst;
   PState *pst_peer[MAXR];
   double fx_scale, fx_inv;  // 2^sh and 2^-sh of the fixed-point statistics
+  long long *trace;         // optional phase trace of CTA 0 (TSGPU_TRACE=1), 64 items x 128 slots
 };
 
 // ------------------------------------------------------------------------------------------
@@ -532,7 +535,7 @@ struct ts_engine {
   Xchg *xchg = nullptr;
   Xbuf *xbuf = nullptr;  // &xchg->x
   bool staged = false;   // TSGPU_PATH=staged: one launch per round (debug cross-check path)
-  int grid_persist = 1, block_persist = 32;
+  int grid_persist = 1, block_persist = 32, ind_per_thread = 1;
   std::vector<void *> ipc_opened;
   // validation set (host copies)
   std::vector<uint32_t> val_loc;         // ascending
@@ -620,11 +623,32 @@ static void launch_heldout(ts_engine *e, unsigned n_items) {
 }
 
 // persistent-kernel launch (cooperative: every CTA must be resident for the grid barrier)
+template <int K, int I>
+static cudaError_t launch_persist_ki(ts_engine *e, uint32_t n_items) {
+  if constexpr (I > tsp::persist_imax(K)) {
+    return cudaErrorInvalidValue;
+  } else {
+    static bool attr_set[64] = {false};
+    const size_t smem = tsp::persist_smem_bytes(K, I);
+    if (!attr_set[e->cfg.device]) {
+      cudaError_t er = cudaFuncSetAttribute(tsp::k_persist<K, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (er != cudaSuccess) return er;
+      attr_set[e->cfg.device] = true;
+    }
+    void *args[] = {(void *)&e->prm, (void *)&n_items};
+    return cudaLaunchCooperativeKernel((const void *)tsp::k_persist<K, I>, dim3(e->grid_persist),
+                                       dim3(e->block_persist), args, smem, e->stream);
+  }
+}
 template <int K>
 static cudaError_t launch_persist_k(ts_engine *e, uint32_t n_items) {
-  void *args[] = {(void *)&e->prm, (void *)&n_items};
-  return cudaLaunchCooperativeKernel((const void *)tsp::k_persist<K>, dim3(e->grid_persist),
-                                     dim3(e->block_persist), args, 0, e->stream);
+  switch (e->ind_per_thread) {
+    case 1: return launch_persist_ki<K, 1>(e, n_items);
+    case 2: return launch_persist_ki<K, 2>(e, n_items);
+    case 3: return launch_persist_ki<K, 3>(e, n_items);
+    case 4: return launch_persist_ki<K, 4>(e, n_items);
+  }
+  return cudaErrorInvalidValue;
 }
 static cudaError_t launch_persist(ts_engine *e, uint32_t n_items) {
   switch (e->K) {
@@ -634,15 +658,6 @@ static cudaError_t launch_persist(ts_engine *e, uint32_t n_items) {
 #undef X
   }
   return cudaErrorInvalidValue;
-}
-static int persist_tmax(int K) {
-  switch (K) {
-#define X(k) \
-  case k: return tsp::Cfg<k>::TMAX;
-    TS_FOR_EACH_K(X)
-#undef X
-  }
-  return 256;
 }
 
 extern "C" {
@@ -746,18 +761,33 @@ int ts_create(const ts_config *cfg, ts_engine **out) {
     // same number of individuals (I = ceil(n / (SMs * TMAX))).
     const char *path = getenv("TSGPU_PATH");
     e->staged = path && !strcmp(path, "staged");
-    const int tmax = persist_tmax(e->K);
+    // I individuals per thread in registers: the smallest I whose thread cap covers the shard.
+    // Shards too large for the register-resident kernel run the staged path.
     const uint64_t n = cfg->n_local;
-    const uint64_t per_thread = (n + (uint64_t)e->num_sms * tmax - 1) / ((uint64_t)e->num_sms * tmax);
-    const uint64_t threads = (n + per_thread - 1) / per_thread;
-    e->grid_persist = (int)std::min<uint64_t>(e->num_sms, (threads + tmax - 1) / tmax);
-    const uint64_t t = (threads + e->grid_persist - 1) / e->grid_persist;
-    e->block_persist = (int)std::min<uint64_t>(tmax, (t + 31) / 32 * 32);
+    int I = 0;
+    const char *force = getenv("TSGPU_IPT");  // developer knob: minimum individuals per thread
+    const int imin = force ? std::max(1, atoi(force)) : 1;
+    for (int c = imin; c <= tsp::persist_imax(e->K); ++c)
+      if ((uint64_t)e->num_sms * tsp::persist_tmax(e->K, c) * c >= n) { I = c; break; }
+    if (I == 0) e->staged = true;
+    else {
+      const int tmax = tsp::persist_tmax(e->K, I);
+      const uint64_t threads = (n + I - 1) / I;
+      e->ind_per_thread = I;
+      e->grid_persist = (int)std::min<uint64_t>(e->num_sms, (threads + 63) / 64);  // all SMs once there are 2 warps each
+      const uint64_t t = (threads + e->grid_persist - 1) / e->grid_persist;
+      e->block_persist = (int)std::min<uint64_t>(tmax, (t + 31) / 32 * 32);
+    }
     int bits = 1;
     while ((2 * cfg->n_total + 2) >> bits) bits++;
-    const int sh = 53 - bits;
+    const int sh = 52 - bits;  // per-warp sums stay below 2^52 (mantissa-trick conversion)
     e->prm.fx_scale = ldexp(1.0, sh);
     e->prm.fx_inv = ldexp(1.0, -sh);
+    e->prm.trace = nullptr;
+    if (getenv("TSGPU_TRACE")) {
+      CKE(dalloc(&e->prm.trace, 64 * 128));
+      CKE(cudaMemset(e->prm.trace, 0, 64 * 128 * sizeof(long long)));
+    }
   }
   CKE(dalloc(&e->partial, (size_t)e->grid_estep * 2 * K));
   e->items_cap = 1 << 16;
@@ -795,6 +825,7 @@ int ts_destroy(ts_engine *e) {
   cudaFree(e->ctl);
   cudaFree(e->items);
   cudaFree(e->xchg);
+  cudaFree(e->prm.trace);
   cudaFree(e->d_voff);
   cudaFree(e->d_vind);
   cudaFree(e->d_val_loc);
@@ -1172,6 +1203,14 @@ int ts_comm_connect_local(ts_engine **engines, int n) {
 }
 
 uint64_t ts_launch_count(const ts_engine *e) { return e ? e->launches : 0; }
+
+int ts_debug_trace(ts_engine *e, long long *out /* 64 x 128 */) {
+  if (!e || !out || !e->prm.trace) return set_err(TS_ERR_STATE, "ts_debug_trace: tracing is off (TSGPU_TRACE=1)");
+  if (use_device(e)) return TS_ERR_CUDA;
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpy(out, e->prm.trace, 64 * 128 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return TS_OK;
+}
 
 int ts_timer_start(ts_engine *e) {
   if (!e) return set_err(TS_ERR_ARG, "ts_timer_start: null engine");

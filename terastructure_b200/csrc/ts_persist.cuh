@@ -7,29 +7,32 @@
 //   per SNP:  warp 0 of every CTA: b[k][t] = f(lambda[loc][k][t]) / f(lambda[k][0]+lambda[k][1]),
 //                                  f = exp o digamma                         (estimate_beta)
 //     per round (<= online_iterations):
-//       every thread: its individuals' E-step, 4K FMA + 2 divisions each   (process, update_lambda_t)
+//       every thread: its individuals' E-step from REGISTERS (E = f(gamma) of up to 4 individuals
+//             per thread stays in registers for the whole launch), 4K FMA + 2 reciprocals each
 //       warp: transposed shuffle reduction of the 2K partial sums (each lane ends with one sum)
-//       CTA:  cross-warp sum through shared memory, one warp per statistic
-//       grid: the CTA sums are added into 2K global accumulators as 98-bit FIXED-POINT integers
-//             (two u64 words, each also counting arrivals in its top 10 bits) with relaxed
-//             red.add -- integer addition is associative, so the total is independent of arrival
-//             order, and the arrival count rides in the same word as the data, so the grid
-//             barrier needs no fence and no separate flag: one L2 round trip to publish, one to
-//             observe.  Accumulators are monotonic (never reset); two sets alternate by round
-//             parity, and every CTA remembers the previous total of each set.
+//       CTA:  every warp converts its 2K sums to 98-bit FIXED-POINT integers (two u64 words);
+//             4K threads add the warps' words -- integer addition is associative, so the total
+//             does not depend on the order of anything
+//       grid: the CTA totals are added into 4K global words with relaxed red.add; each word also
+//             counts arrivals in its top 10 bits, so the grid barrier needs no fence and no
+//             separate flag: one L2 round trip to publish, one to observe.  The words are
+//             monotonic (never reset); two sets alternate by round parity and every CTA remembers
+//             the previous total of each set.  One lane per CTA spins (on the last word); the
+//             others read their words once that one is complete.  Words sit 1 KB apart so that
+//             they spread over the L2 slices.
 //       multi-GPU: CTA 0 stores the GPU's integer totals (tagged with the round number) into its
 //             slot on every peer over NVLink; every CTA of every GPU adds the slots in rank order.
 //       warp 0 of every CTA (redundantly, bit-identically): lambda, convergence test, new b
 //     gamma step + E = f(gamma) refresh for the CTA's individuals (skipped in hol mode)
 //
-// No host round trip, no kernel launch and no fence inside the batch.
+// No host round trip, no kernel launch and no fence on the critical path of a round.
 #pragma once
 
 namespace tsp {
 
-constexpr int FX_LO_BITS = 44;
 constexpr int FX_CNT_SHIFT = 54;
 constexpr unsigned long long FX_MASK = (1ull << FX_CNT_SHIFT) - 1;
+constexpr double FX_LO_SCALE = 17592186044416.0;  // 2^44
 constexpr long long SPIN_LIMIT = 1ll << 23;
 
 // one level of the transposed reduction: lanes whose `bit` is clear keep the low half of the
@@ -77,7 +80,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-// 1/s for s > 0, normal: MUFU.RCP64H seed (~20 bits) + two Newton steps; <= 1 ulp-ish, which is
+// 1/s for s > 0, normal: MUFU.RCP64H seed (~20 bits) + two Newton steps; within ~1 ulp, which is
 // all the 1e-6 contract (and the 1e-9 test tolerance) can see.  The IEEE division it replaces
 // costs ~4x as many FP64-pipe slots per individual and round.
 __device__ __forceinline__ double fast_rcp(double s) {
@@ -90,18 +93,97 @@ __device__ __forceinline__ double fast_rcp(double s) {
   return r;
 }
 
-template <int K>
-struct Cfg {
-  static constexpr int TMAX = (K <= 6) ? 768 : (K <= 12 ? 512 : (K <= 16 ? 384 : 256));
-};
+// f(x) = exp(digamma(x)) without any table: every coefficient is an immediate, so a warp whose
+// lanes hold unrelated arguments still executes one instruction stream with no memory traffic
+// (the polynomial-table variant in ts_math.cuh needs 104 bytes of coefficients PER LANE and was
+// LSU-bound in shared as well as in global memory).
+//   x >= 8 : asymptotic series f(x) = x - 1/2 + sum_{j>=2} g_j x^(1-j), through j = 16 (error < 3e-16)
+//   x <  8 : f(x) = f(x+8) * exp(-(1/x + ... + 1/(x+7))); the harmonic sum is P'(x)/P(x) with
+//            P(x) = x(x+1)...(x+7) (all coefficients positive: no cancellation)
+// Max relative error 5.5e-15 on [0.03, 1e7] (tools/dev check against mpmath), dominated by the
+// argument of the exp at the small end.
+// exp(-r) for r >= 0 (the only case needed): k = rint(-r*log2(e)), Cody-Waite reduction, degree-11
+// Taylor polynomial on |t| <= ln2/2 (truncation 2e-17), 2^k applied through the exponent field.
+// Arguments beyond 700 flush to zero (exp(psi(x)) for x < 1.4e-3 is below 1e-300).
+__device__ __forceinline__ double exp_neg(double r) {
+  if (r > 700.0) return 0.0;
+  const double kd = fma(-r, 1.4426950408889634, 6755399441055744.0);  // 2^52+2^51: rint in the mantissa
+  const int k = __double2loint(kd);
+  const double kf = kd - 6755399441055744.0;
+  double t = fma(kf, -0.693147180369123816490, -r);   // ln2 split: high part has 11 trailing zero bits
+  t = fma(kf, -1.90821492927058770002e-10, t);
+  const double t2 = t * t;
+  // Estrin: p = sum_{j=0}^{11} t^j / j!
+  const double p01 = 1.0 + t, p23 = fma(t, 1.0 / 6, 0.5), p45 = fma(t, 1.0 / 120, 1.0 / 24),
+               p67 = fma(t, 1.0 / 5040, 1.0 / 720), p89 = fma(t, 1.0 / 362880, 1.0 / 40320),
+               pab = fma(t, 1.0 / 39916800, 1.0 / 3628800);
+  const double t4 = t2 * t2;
+  const double q0 = fma(p23, t2, p01), q1 = fma(p67, t2, p45), q2 = fma(pab, t2, p89);
+  const double p = fma(fma(q2, t4, q1), t4, q0);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
 
-template <int K>
-__global__ void __launch_bounds__(Cfg<K>::TMAX, 1) k_persist(Params p, uint32_t n_items) {
+__device__ __forceinline__ double f_expsi(double x) {
+  const bool small = x < 8.0;
+  const double xs = small ? x + 8.0 : x;
+  const double u = fast_rcp(xs);
+  // q(u) = g2 + g3 u + ... + g16 u^14, Estrin (dependent DFMA latency on B200 is ~23 cycles)
+  const double u2 = u * u;
+  const double a0 = fma(0x1.5555555555555p-6, u, 0x1.5555555555555p-5);
+  const double a1 = fma(-0x1.2222222222222p-8, u, 0x1.05b05b05b05b0p-8);
+  const double a2 = fma(0x1.1a4cc13ddafa2p-9, u, -0x1.c7f80db9bf2a3p-9);
+  const double a3 = fma(-0x1.1e6ee98a17aecp-9, u, 0x1.05f536517fa45p-8);
+  const double a4 = fma(0x1.fe414efb9852ap-9, u, -0x1.e5f884ccda9f9p-8);
+  const double a5 = fma(-0x1.5f836e8779d89p-7, u, 0x1.54c7f9f55e0ebp-6);
+  const double a6 = fma(0x1.59488e35cad4dp-5, u, -0x1.51ea52a4cdfabp-4);
+  const double a7 = 0x1.c276c25d1fbddp-2;
+  const double u4 = u2 * u2;
+  const double b0 = fma(a1, u2, a0), b1 = fma(a3, u2, a2), b2 = fma(a5, u2, a4), b3 = fma(a7, u2, a6);
+  const double u8 = u4 * u4;
+  const double c0 = fma(b1, u4, b0), c1 = fma(b3, u4, b2);
+  const double q = fma(c1, u8, c0);
+  double f = fma(u, q, xs - 0.5);
+  if (small) {
+    // P = x(x+1)...(x+7), D = P'; even/odd split halves the dependency chains
+    const double x2 = x * x;
+    const double pe = fma(fma(fma(x2 + 322.0, x2, 6769.0), x2, 13068.0), x2, 0.0);          // x^8+322x^6+6769x^4+13068x^2
+    const double po = fma(fma(fma(28.0, x2, 1960.0), x2, 13132.0), x2, 5040.0);              // 28x^6+1960x^4+13132x^2+5040 (times x)
+    const double de = fma(fma(fma(196.0, x2, 9800.0), x2, 39396.0), x2, 5040.0);             // 196x^6+9800x^4+39396x^2+5040
+    const double dod = fma(fma(fma(8.0, x2, 1932.0), x2, 27076.0), x2, 26136.0);             // 8x^6+1932x^4+27076x^2+26136 (times x)
+    const double P = fma(po, x, pe), D = fma(dod, x, de);
+    f *= exp_neg(D * fast_rcp(P));
+  }
+  return f;
+}
+
+// Optional phase trace (TSGPU_TRACE=1): CTA 0 / thread 0 stamps clock64() at phase boundaries.
+#define TS_TRACE(slot)                                                                        \
+  do {                                                                                        \
+    if (p.trace && blockIdx.x == 0 && tid == 0 && i < 64)                                     \
+      p.trace[(size_t)i * 128 + (slot)] = clock64();                                          \
+  } while (0)
+
+// I individuals per thread live in registers; threads per CTA are capped so that the register
+// file holds them.  Combinations that are not instantiated fall back to the staged path.
+__host__ __device__ constexpr int persist_imax(int K) { return K <= 12 ? 4 : (K <= 20 ? 2 : 1); }
+__host__ __device__ constexpr int persist_tmax(int K, int I) {
+  return K <= 12 ? (I == 1 ? 512 : (I == 2 ? 384 : (I == 3 ? 288 : 256)))
+                 : (K <= 20 ? (I == 1 ? 384 : 256) : 256);
+}
+__host__ __device__ constexpr size_t persist_smem_bytes(int K, int I) {
+  return sizeof(double) * (4 * K) + sizeof(long long) * (4 * K * (persist_tmax(K, I) / 32 + 1)) + 16;
+}
+
+template <int K, int I>
+__global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uint32_t n_items) {
   constexpr int V = 2 * K;
+  constexpr int NW = 2 * V;           // fixed-point words per round: word = hl * V + v
   constexpr int VPL = (V + 31) / 32;  // statistics per lane of the control warp
-  __shared__ double s_bcur[V], s_bprev[V];
-  __shared__ double s_red[V][33];
-  __shared__ int s_flag;  // bit 0: round loop done, bit 1: abort (peer or CTA lost)
+  constexpr int WS = persist_tmax(K, I) / 32 + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *s_b = reinterpret_cast<double *>(smem_raw);                // [2][V]: b of round x at [x&1]
+  long long *s_fix = reinterpret_cast<long long *>(s_b + 2 * V);     // [NW][WS] per-warp fixed-point words
+  int *s_flag = reinterpret_cast<int *>(s_fix + NW * WS);  // bit 0: round loop done, bit 1: abort
 
   PState *st = p.pst;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
@@ -122,7 +204,7 @@ __global__ void __launch_bounds__(Cfg<K>::TMAX, 1) k_persist(Params p, uint32_t 
     }
   }
 
-  // control-warp state: previous totals of the two accumulator sets, current lambda row
+  // control-warp state: previous totals of the two word sets, current lambda row
   unsigned long long ph0[VPL], pl0[VPL], ph1[VPL], pl1[VPL];
   double lam[VPL];
   unsigned long long rc = st->round_ctr;
@@ -131,22 +213,39 @@ __global__ void __launch_bounds__(Cfg<K>::TMAX, 1) k_persist(Params p, uint32_t 
     for (int q = 0; q < VPL; ++q) {
       const int v = lane + 32 * q;
       const bool act = v < V;
-      ph0[q] = act ? st->prev[0][0][v] : 0;
-      pl0[q] = act ? st->prev[0][1][v] : 0;
-      ph1[q] = act ? st->prev[1][0][v] : 0;
-      pl1[q] = act ? st->prev[1][1][v] : 0;
-      lam[q] = 1.0;
+      ph0[q] = act ? st->prev[0][v] : 0;
+      pl0[q] = act ? st->prev[0][V + v] : 0;
+      ph1[q] = act ? st->prev[1][v] : 0;
+      pl1[q] = act ? st->prev[1][V + v] : 0;
+      lam[q] = 1024.0;  // idle lanes hold a large dummy so they never take f's small-argument path
     }
   }
   uint32_t prev_loc = 0xffffffffu;
 
+  // this thread's individuals and their E = exp(psi(gamma)) rows, register-resident
+  uint32_t nj[I];
+  bool valid[I];
+  double e[I][K];
+#pragma unroll
+  for (int j = 0; j < I; ++j) {
+    nj[j] = gtid + (uint32_t)j * GT;
+    valid[j] = nj[j] < p.n_local;
+#pragma unroll
+    for (int k = 0; k < K; ++k) e[j][k] = valid[j] ? p.E[(size_t)k * p.npad + nj[j]] : 0.0;
+  }
+  __syncthreads();
+
   for (uint32_t i = 0; i < n_items; ++i) {
     const WorkItem it = p.items[i];
     const unsigned char *col = it.col;
+    int code[I];
+#pragma unroll
+    for (int j = 0; j < I; ++j) code[j] = valid[j] ? tsm::plink_code(col, nj[j]) : 1;
     if (i + 1 < n_items) {  // next SNP's genotype column and lambda row -> L2
       const WorkItem nx = p.items[i + 1];
-      for (uint32_t n = gtid; n < p.n_local; n += GT)
-        if ((n & 511) == 0) prefetch_l2(nx.col + (n >> 2));  // one request per 128-byte line
+#pragma unroll
+      for (int j = 0; j < I; ++j)
+        if (valid[j] && (nj[j] & 511) == 0) prefetch_l2(nx.col + (nj[j] >> 2));  // one per 128-byte line
       if (warp == 0 && lane < V) prefetch_l2(p.lambda + (size_t)nx.loc * V + lane);
     }
     if (warp == 0) {
@@ -154,7 +253,7 @@ __global__ void __launch_bounds__(Cfg<K>::TMAX, 1) k_persist(Params p, uint32_t 
 #pragma unroll
       for (int q = 0; q < VPL; ++q) {
         const int v = lane + 32 * q;
-        if (it.loc != prev_loc) lam[q] = (v < V) ? __ldcg(p.lambda + (size_t)it.loc * V + v) : 1.0;
+        if (it.loc != prev_loc) lam[q] = (v < V) ? __ldcg(p.lambda + (size_t)it.loc * V + v) : 1024.0;
         own[q] = lam[q];
       }
 #pragma unroll
@@ -165,66 +264,123 @@ __global__ void __launch_bounds__(Cfg<K>::TMAX, 1) k_persist(Params p, uint32_t 
         double s = 0.0;
         s += l0;
         s += l1;
-        const double b = tsm::exp_digamma_tab(own[q]) / tsm::exp_digamma_tab(s);
-        if (v < V) { s_bcur[v] = b; s_bprev[v] = b; }
+        const double b = f_expsi(own[q]) * fast_rcp(f_expsi(s));
+        if (v < V) s_b[v] = b;
       }
-      if (lane == 0) s_flag = 0;
+      if (lane == 0) *s_flag = 0;
     }
     prev_loc = it.loc;
+    TS_TRACE(0);
     __syncthreads();
+    TS_TRACE(1);
 
     uint32_t x = 0;
+    double r0[I], r1[I];
+    bool gamma_done = false;
+    // ---- gamma natural-gradient step + E refresh (update_gamma/estimate_theta, cc:695-740) ----
+    // phi of the LAST E-step: r0/r1 are still in registers, `bl` is the b that E-step used.
+    auto gamma_step = [&](const double *bl) {
+#pragma unroll
+      for (int j = 0; j < I; ++j) {
+        if (code[j] == 1) continue;
+        const uint32_t n = nj[j];
+        const uint32_t cn = p.cnt[n];
+        double g[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) g[k] = p.gamma[(size_t)k * p.npad + n];
+        const double base = p.nodetau0 + (double)cn;
+        const double rho = (p.nodekappa == 0.5) ? rsqrt(base) : pow(base, -p.nodekappa);
+        p.cnt[n] = cn + 1;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const double2 bk = *reinterpret_cast<const double2 *>(bl + 2 * k);
+          // y*phimom + (2-y)*phidad = E[k] * (b0[k]*y/s0 + b1[k]*(2-y)/s1)
+          const double w = e[j][k] * fma(bk.x, r0[j], bk.y * r1[j]);
+          const double gn = g[k] + rho * (p.alpha + p.lscale * w - g[k]);
+          p.gamma[(size_t)k * p.npad + n] = gn;
+          e[j][k] = f_expsi(gn);
+        }
+      }
+      if (i + 1 == n_items) {  // E leaves the registers only at the end of the launch
+#pragma unroll
+        for (int j = 0; j < I; ++j)
+          if (valid[j]) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) p.E[(size_t)k * p.npad + nj[j]] = e[j][k];
+          }
+      }
+    };
     while (true) {
-      // ---- E-step over this thread's individuals -------------------------------------------
+      const double *bx = s_b + (x & 1) * V;
+      // ---- E-step over this thread's individuals: registers + broadcast shared-memory b --------
       double vv[V];
 #pragma unroll
       for (int v = 0; v < V; ++v) vv[v] = 0.0;
-      for (uint32_t n = gtid; n < p.n_local; n += GT) {
-        // missing or held out (kv_ok, hh:389-408) -> weight 0; branch-free so the warp stays converged
-        const int code = tsm::plink_code(col, n);
-        const int y = tsm::code_to_y(code);
-        const double w0 = (code == 1) ? 0.0 : (double)y, w1 = (code == 1) ? 0.0 : (double)(2 - y);
-        double e[K], s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < I; ++j) {
+        // missing or held out (kv_ok, hh:389-408) -> weight 0; branch-free, the warp stays converged
+        const int y = tsm::code_to_y(code[j]);
+        const double w0 = (code[j] == 1) ? 0.0 : (double)y, w1 = (code[j] == 1) ? 0.0 : (double)(2 - y);
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          e[k] = p.E[(size_t)k * p.npad + n];
-          s0 = fma(e[k], s_bcur[2 * k], s0);
-          s1 = fma(e[k], s_bcur[2 * k + 1], s1);
+          const double2 bk = *reinterpret_cast<const double2 *>(bx + 2 * k);
+          s0 = fma(e[j][k], bk.x, s0);
+          s1 = fma(e[j][k], bk.y, s1);
         }
-        const double r0 = w0 * fast_rcp(s0), r1 = w1 * fast_rcp(s1);
+        // padding threads (no individual) have e = 0, s = 0: keep the reciprocal finite
+        r0[j] = w0 * fast_rcp(valid[j] ? s0 : 1.0);
+        r1[j] = w1 * fast_rcp(valid[j] ? s1 : 1.0);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          vv[2 * k] = fma(e[k], r0, vv[2 * k]);
-          vv[2 * k + 1] = fma(e[k], r1, vv[2 * k + 1]);
+          vv[2 * k] = fma(e[j][k], r0[j], vv[2 * k]);
+          vv[2 * k + 1] = fma(e[j][k], r1[j], vv[2 * k + 1]);
         }
       }
-      // ---- warp: transposed reduction; CTA: one warp per statistic --------------------------
-      // The loop above has a lane-dependent trip count; reconverge the warp explicitly before the
-      // shuffles (shfl.sync requires every named lane to execute the SAME instruction, and the
-      // compiler is free to duplicate the loop tail).
-      __syncwarp();
+      TS_TRACE(2 + 8 * x + 0);
+      // ---- warp: transposed reduction; every warp hands its sums over as fixed point -----------
       tr_reduce<V>(vv, lane);
 #pragma unroll
       for (int q = 0; q < VPL; ++q)
-        if (q < tr_len) s_red[tr_start + q][warp] = vv[q];
-      __syncthreads();
-      const int par = (int)(rc & 1);
-      for (int v = warp; v < V; v += W) {
-        double t = (lane < W) ? s_red[v][lane] : 0.0;
-        t = warp_sum(t);
-        if (lane == 0) {
-          // S_t[k] contribution of this CTA, as hi * 2^-sh + lo * 2^-(sh+44)
-          const double sc = (s_bcur[v] * t) * p.fx_scale;
-          const unsigned long long hi = __double2ull_rd(sc);
-          const double rem = sc - (double)hi;
-          const unsigned long long lo = __double2ull_rn(rem * 17592186044416.0);
-          red_add(&st->acc[par][0][v], hi + (1ull << FX_CNT_SHIFT));
-          red_add(&st->acc[par][1][v], lo + (1ull << FX_CNT_SHIFT));
+        if (q < tr_len) {
+          const int v = tr_start + q;
+          // S_t[k] contribution of this warp = hi * 2^-sh + lo * 2^-(sh+44), hi = rint(sc) >= 0,
+          // |lo| <= 2^43; both conversions are "add 2^52 and read the mantissa" (sc < 2^52)
+          const double sc = (bx[v] * vv[q]) * p.fx_scale;
+          const double th = sc + 4503599627370496.0;
+          const double rem = sc - (th - 4503599627370496.0);
+          const double tl = fma(rem, FX_LO_SCALE, 6755399441055744.0);  // 2^52 + 2^51: signed
+          s_fix[v * WS + warp] = __double_as_longlong(th) - 0x4330000000000000ll;
+          s_fix[(V + v) * WS + warp] = __double_as_longlong(tl) - 0x4338000000000000ll;
         }
+      TS_TRACE(2 + 8 * x + 1);
+      __syncthreads();
+      TS_TRACE(2 + 8 * x + 2);
+      const int par = (int)(rc & 1);
+      for (int v = tid; v < V; v += blockDim.x) {  // add the warps' words, publish with arrival count 1
+        const long long *sh = s_fix + v * WS, *sl = s_fix + (V + v) * WS;
+        long long hi = 0, lo = 0;
+#pragma unroll
+        for (int ww = 0; ww < WS - 1; ++ww)
+          if (ww < W) { hi += sh[ww]; lo += sl[ww]; }
+        const long long carry = lo >> 44;  // floor: the low word becomes [0, 2^44)
+        hi += carry;
+        lo -= carry << 44;
+        red_add(&st->acc[par][v][0], (unsigned long long)hi + (1ull << FX_CNT_SHIFT));
+        red_add(&st->acc[par][V + v][0], (unsigned long long)lo + (1ull << FX_CNT_SHIFT));
+      }
+      TS_TRACE(2 + 8 * x + 3);
+      // The last round's totals only feed lambda[loc] (the gamma step uses the phi of THIS E-step),
+      // so when this round is known to be the last one the gamma step runs now, in the shadow of
+      // the grid barrier, and the control warp collects the totals afterwards.
+      if (x + 1 >= p.max_rounds && !(it.flags & ITEM_HOL)) {
+        gamma_step(bx);
+        gamma_done = true;
       }
       // ---- control warp: grid barrier + totals, lambda update, convergence, new b -------------
       if (warp == 0) {
-        double tot[VPL], chg = 0.0;
+        __syncwarp();  // the gamma step above has lane-dependent control flow
+        double tot[VPL];
         bool abort = false;
 #pragma unroll
         for (int q = 0; q < VPL; ++q) {
@@ -234,8 +390,8 @@ __global__ void __launch_bounds__(Cfg<K>::TMAX, 1) k_persist(Params p, uint32_t 
             const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q];
             long long spins = 0;
             while (true) {
-              dh = ld_relaxed(&st->acc[par][0][v]) - bh;
-              dl = ld_relaxed(&st->acc[par][1][v]) - bl;
+              dh = ld_relaxed(&st->acc[par][v][0]) - bh;
+              dl = ld_relaxed(&st->acc[par][V + v][0]) - bl;
               if ((dh >> FX_CNT_SHIFT) == G && (dl >> FX_CNT_SHIFT) == G) break;
               if (++spins > SPIN_LIMIT) { abort = true; break; }
             }
@@ -246,16 +402,16 @@ __global__ void __launch_bounds__(Cfg<K>::TMAX, 1) k_persist(Params p, uint32_t 
               const unsigned long long tag = ((rc + 1) & 1023ull) << FX_CNT_SHIFT;
               if (blockIdx.x == 0)
                 for (int r = 0; r < p.nranks; ++r) {
-                  st_relaxed_sys(&p.pst_peer[r]->slot[p.rank][par][0][v], tag | dh);
-                  st_relaxed_sys(&p.pst_peer[r]->slot[p.rank][par][1][v], tag | dl);
+                  st_relaxed_sys(&p.pst_peer[r]->slot[p.rank][par][v], tag | dh);
+                  st_relaxed_sys(&p.pst_peer[r]->slot[p.rank][par][V + v], tag | dl);
                 }
               unsigned long long th = 0, tl = 0;
               for (int r = 0; r < p.nranks && !abort; ++r) {
                 unsigned long long wh, wl;
                 spins = 0;
                 while (true) {
-                  wh = ld_relaxed_sys(&st->slot[r][par][0][v]);
-                  wl = ld_relaxed_sys(&st->slot[r][par][1][v]);
+                  wh = ld_relaxed_sys(&st->slot[r][par][v]);
+                  wl = ld_relaxed_sys(&st->slot[r][par][V + v]);
                   if ((wh & ~FX_MASK) == tag && (wl & ~FX_MASK) == tag) break;
                   if (++spins > SPIN_LIMIT) { abort = true; break; }
                 }
@@ -266,79 +422,64 @@ __global__ void __launch_bounds__(Cfg<K>::TMAX, 1) k_persist(Params p, uint32_t 
               dl = tl;
             }
           }
-          tot[q] = ((double)dh + (double)dl * (1.0 / 17592186044416.0)) * p.fx_inv;
+          // u64 -> double through the mantissa (both < 2^52): one integer OR and one DADD each
+          const double dhd = __longlong_as_double((long long)(dh | 0x4330000000000000ull)) - 4503599627370496.0;
+          const double dld = __longlong_as_double((long long)(dl | 0x4330000000000000ull)) - 4503599627370496.0;
+          tot[q] = fma(dld, 1.0 / FX_LO_SCALE, dhd) * p.fx_inv;
         }
-        abort = __any_sync(0xffffffffu, abort);
-        double own[VPL];
+        TS_TRACE(2 + 8 * x + 4);
+        // new lambda -> new b first (the critical path of the round); convergence test afterwards
+        double own[VPL], oldlam[VPL];
+        double *bn = s_b + ((x + 1) & 1) * V;
 #pragma unroll
         for (int q = 0; q < VPL; ++q) {
           const int v = lane + 32 * q;
-          const double nl = ((v & 1) ? p.eta1 : p.eta0) + tot[q];  // update_lambda (cc:267-277)
-          if (v < V) chg += fabs(nl - lam[q]);
-          if (v < V) lam[q] = nl;
-          own[q] = lam[q];
-        }
-        chg = warp_sum(chg);
-        const bool done = (chg / (double)V < p.thresh) || (x + 1 >= p.max_rounds);  // cc:359-365
-#pragma unroll
-        for (int q = 0; q < VPL; ++q) {
-          const int v = lane + 32 * q;
+          oldlam[q] = lam[q];
+          own[q] = (v < V) ? ((v & 1) ? p.eta1 : p.eta0) + tot[q] : 1024.0;  // update_lambda (cc:267-277); idle lanes: any large value
+          lam[q] = own[q];
+          const double fo = f_expsi(own[q]);
           const double other = __shfl_xor_sync(0xffffffffu, own[q], 1);
           const double l0 = (v & 1) ? other : own[q], l1 = (v & 1) ? own[q] : other;
           double s = 0.0;
           s += l0;
           s += l1;
-          const double b = tsm::exp_digamma_tab(own[q]) / tsm::exp_digamma_tab(s);  // estimate_beta
-          if (v < V) {
-            s_bprev[v] = s_bcur[v];
-            s_bcur[v] = b;
-            if (done && blockIdx.x == 0) p.lambda[(size_t)it.loc * V + v] = own[q];
-          }
+          const double b = fo * fast_rcp(f_expsi(s));  // estimate_beta (cc:279-296)
+          if (v < V) bn[v] = b;
+        }
+        double chg = 0.0;
+#pragma unroll
+        for (int q = 0; q < VPL; ++q)
+          if (lane + 32 * q < V) chg += fabs(own[q] - oldlam[q]);
+        chg = warp_sum(chg);
+        abort = __any_sync(0xffffffffu, abort);
+        const bool done = (chg / (double)V < p.thresh) || (x + 1 >= p.max_rounds);  // cc:359-365
+        if (done && blockIdx.x == 0) {
+#pragma unroll
+          for (int q = 0; q < VPL; ++q)
+            if (lane + 32 * q < V) p.lambda[(size_t)it.loc * V + lane + 32 * q] = own[q];
         }
         if (lane == 0) {
-          if (abort) { st->fault = 1; s_flag = 2; }
-          else if (done) s_flag = 1;
+          if (abort) { st->fault = 1; *s_flag = 2; }
+          else if (done) *s_flag = 1;
           if (done && blockIdx.x == 0) p.rounds[i] = x + 1;
         }
-        if (done && blockIdx.x == 0) __threadfence();  // lambda row visible before any later reader
+        TS_TRACE(2 + 8 * x + 5);
       }
       __syncthreads();
+      TS_TRACE(2 + 8 * x + 6);
       ++x;
       ++rc;
-      const int flag = s_flag;
+      const int flag = *s_flag;
       if (flag & 2) return;
       if (flag & 1) break;
     }
 
-    // ---- gamma natural-gradient step + E refresh (update_gamma/estimate_theta, cc:695-740) ----
-    if (!(it.flags & ITEM_HOL)) {
-      for (uint32_t n = gtid; n < p.n_local; n += GT) {
-        const int code = tsm::plink_code(col, n);
-        if (code == 1) continue;
-        const int y = tsm::code_to_y(code);
-        double e[K], s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          e[k] = p.E[(size_t)k * p.npad + n];
-          s0 = fma(e[k], s_bprev[2 * k], s0);
-          s1 = fma(e[k], s_bprev[2 * k + 1], s1);
-        }
-        const double r0 = (double)y * fast_rcp(s0), r1 = (double)(2 - y) * fast_rcp(s1);
-        const uint32_t cn = p.cnt[n];
-        const double base = p.nodetau0 + (double)cn;
-        const double rho = (p.nodekappa == 0.5) ? rsqrt(base) : pow(base, -p.nodekappa);
-        p.cnt[n] = cn + 1;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const double g = p.gamma[(size_t)k * p.npad + n];
-          const double w = e[k] * fma(s_bprev[2 * k], r0, s_bprev[2 * k + 1] * r1);
-          const double gn = g + rho * (p.alpha + p.lscale * w - g);
-          p.gamma[(size_t)k * p.npad + n] = gn;
-          p.E[(size_t)k * p.npad + n] = tsm::exp_digamma_tab(gn);
-        }
-      }
-    }
-    __syncthreads();  // s_bprev/s_bcur are rewritten for the next SNP
+    // early-converged SNPs take the gamma step here; the usual case (all rounds run) took it
+    // inside the last round, in the shadow of that round's grid barrier
+    if (!gamma_done && !(it.flags & ITEM_HOL)) gamma_step(s_b + ((x - 1) & 1) * V);
+    TS_TRACE(100);
+    __syncthreads();  // s_b is rewritten for the next SNP
+    TS_TRACE(101);
   }
 
   if (blockIdx.x == 0 && warp == 0) {
@@ -346,10 +487,10 @@ __global__ void __launch_bounds__(Cfg<K>::TMAX, 1) k_persist(Params p, uint32_t 
     for (int q = 0; q < VPL; ++q) {
       const int v = lane + 32 * q;
       if (v < V) {
-        st->prev[0][0][v] = ph0[q];
-        st->prev[0][1][v] = pl0[q];
-        st->prev[1][0][v] = ph1[q];
-        st->prev[1][1][v] = pl1[q];
+        st->prev[0][v] = ph0[q];
+        st->prev[0][V + v] = pl0[q];
+        st->prev[1][v] = ph1[q];
+        st->prev[1][V + v] = pl1[q];
       }
     }
     if (lane == 0) st->round_ctr = rc;
