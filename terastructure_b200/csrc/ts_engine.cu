@@ -95,7 +95,7 @@ struct PState {
   // 1 KB so that the 4K words of a round spread over the L2 slices
   unsigned long long acc[2][4 * MAXK][128];
   unsigned long long prev[2][4 * MAXK];        // totals at the end of the previous launch
-  unsigned long long slot[MAXR][2][4 * MAXK];  // [source rank][parity][word], peer-written
+  unsigned long long slot[MAXR][2][4 * MAXK][32];  // [source rank][parity][word][0], peer-written, 256 B apart
   unsigned long long round_ctr;                // rounds run so far (slot tags; same on every rank)
   uint32_t fault;
   uint32_t pad;
@@ -135,6 +135,7 @@ struct Params {
   PState *pst;
   PState *pst_peer[MAXR];
   double fx_scale, fx_inv;  // 2^sh and 2^-sh of the fixed-point statistics
+  int xflush;               // fence.sys after the peer stores (TSGPU_XFLUSH, default on)
   long long *trace;         // optional phase trace of CTA 0 (TSGPU_TRACE=1), 64 items x 128 slots
 };
 
@@ -784,6 +785,7 @@ int ts_create(const ts_config *cfg, ts_engine **out) {
     e->prm.fx_scale = ldexp(1.0, sh);
     e->prm.fx_inv = ldexp(1.0, -sh);
     e->prm.trace = nullptr;
+    e->prm.xflush = getenv("TSGPU_XFLUSH") ? atoi(getenv("TSGPU_XFLUSH")) : 1;
     if (getenv("TSGPU_TRACE")) {
       CKE(dalloc(&e->prm.trace, 64 * 128));
       CKE(cudaMemset(e->prm.trace, 0, 64 * 128 * sizeof(long long)));

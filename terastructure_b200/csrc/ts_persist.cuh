@@ -387,31 +387,38 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
           const int v = lane + 32 * q;
           unsigned long long dh = 0, dl = 0;
           if (v < V) {
-            const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q];
             long long spins = 0;
-            while (true) {
-              dh = ld_relaxed(&st->acc[par][v][0]) - bh;
-              dl = ld_relaxed(&st->acc[par][V + v][0]) - bl;
-              if ((dh >> FX_CNT_SHIFT) == G && (dl >> FX_CNT_SHIFT) == G) break;
-              if (++spins > SPIN_LIMIT) { abort = true; break; }
+            // single GPU: every CTA waits for the local words.  Several GPUs: only CTA 0 does (it
+            // forwards the GPU's totals); the other CTAs wait for the rank slots alone, which keeps
+            // the pollers off the words the arrivals are being added to.
+            if (p.nranks == 1 || blockIdx.x == 0) {
+              const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q];
+              while (true) {
+                dh = ld_relaxed(&st->acc[par][v][0]) - bh;
+                dl = ld_relaxed(&st->acc[par][V + v][0]) - bl;
+                if ((dh >> FX_CNT_SHIFT) == G && (dl >> FX_CNT_SHIFT) == G) break;
+                if (++spins > SPIN_LIMIT) { abort = true; break; }
+              }
+              if (par) { ph1[q] = bh + dh; pl1[q] = bl + dl; } else { ph0[q] = bh + dh; pl0[q] = bl + dl; }
+              dh &= FX_MASK;
+              dl &= FX_MASK;
             }
-            if (par) { ph1[q] = bh + dh; pl1[q] = bl + dl; } else { ph0[q] = bh + dh; pl0[q] = bl + dl; }
-            dh &= FX_MASK;
-            dl &= FX_MASK;
             if (p.nranks > 1) {
               const unsigned long long tag = ((rc + 1) & 1023ull) << FX_CNT_SHIFT;
-              if (blockIdx.x == 0)
+              if (blockIdx.x == 0) {
                 for (int r = 0; r < p.nranks; ++r) {
-                  st_relaxed_sys(&p.pst_peer[r]->slot[p.rank][par][v], tag | dh);
-                  st_relaxed_sys(&p.pst_peer[r]->slot[p.rank][par][V + v], tag | dl);
+                  st_relaxed_sys(&p.pst_peer[r]->slot[p.rank][par][v][0], tag | dh);
+                  st_relaxed_sys(&p.pst_peer[r]->slot[p.rank][par][V + v][0], tag | dl);
                 }
+                if (p.xflush) __threadfence_system();  // push the NVLink writes out now
+              }
               unsigned long long th = 0, tl = 0;
               for (int r = 0; r < p.nranks && !abort; ++r) {
                 unsigned long long wh, wl;
                 spins = 0;
                 while (true) {
-                  wh = ld_relaxed_sys(&st->slot[r][par][v]);
-                  wl = ld_relaxed_sys(&st->slot[r][par][V + v]);
+                  wh = ld_relaxed_sys(&st->slot[r][par][v][0]);
+                  wl = ld_relaxed_sys(&st->slot[r][par][V + v][0]);
                   if ((wh & ~FX_MASK) == tag && (wl & ~FX_MASK) == tag) break;
                   if (++spins > SPIN_LIMIT) { abort = true; break; }
                 }
