@@ -206,15 +206,18 @@ def main():
     ap.add_argument("--individuals", type=int, default=0, help="override individuals per GPU (debug)")
     ap.add_argument("--snps", type=int, default=0, help="override L (debug)")
     ap.add_argument("--batch", type=int, default=0, help="override SVI iterations per step (debug/profiling)")
+    ap.add_argument("--k", type=int, default=0, help="override K (BASELINE configs[4] sweep)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
     if args.warmup < 3:
         args.warmup = 3
-    global BATCH
+    global BATCH, K
     if args.batch:
         BATCH = args.batch
+    if args.k:
+        K = args.k
 
     import torch
     import torch.distributed as dist
@@ -309,8 +312,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world) if not (args.individuals or args.snps or args.batch) else
-            {"workload": f"DEBUG override: {n_total} x {l}, K={K}", "svi_iterations_per_step": BATCH},
+            "config": workload_config(world) if not (args.individuals or args.snps or args.batch or args.k) else
+            {"workload": f"override: {n_total} individuals x {l} SNPs, K={K}", "individuals": n_total, "snps": l, "K": K,
+             "svi_iterations_per_step": BATCH},
             "clocks": clocks,
             "e2e": {"value": genos / e2e_s, "unit": UNIT, "h2d_bytes_per_step": BATCH * 24,
                     "d2h_bytes_per_step": BATCH * 4,

@@ -1,0 +1,107 @@
+// Device-side structures shared by the kernels of libtsgpu.so (ts_engine.cu, ts_persist_inst.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "ts_math.cuh"
+#include "tsgpu.h"
+
+// ------------------------------------------------------------------------------------------
+// device-side structures
+// ------------------------------------------------------------------------------------------
+enum : uint32_t { ITEM_HOL = 1u, ITEM_FIRST = 2u };
+
+struct WorkItem {
+  const unsigned char *col;  // packed column the E-step/gamma step read (bed row or vcol row)
+  uint32_t loc;
+  int32_t vslot;  // index among validation loci, or -1
+  uint32_t flags;
+  uint32_t pad;
+};
+
+constexpr int MAXK = TS_MAX_K;
+constexpr int MAXR = 16;  // ranks in one exchange group
+
+struct Ctl {
+  long long cursor;  // index of the work item being processed
+  uint32_t x;        // rounds completed for the current item
+  uint32_t done;     // round loop finished
+  uint32_t ticket;   // last-CTA-done counter of k_estep
+  uint32_t epoch;    // exchange epoch (multi-GPU)
+  uint32_t fault;    // set when a peer wait timed out
+  uint32_t pad;
+  double bcur[2 * MAXK];   // exp(Elogbeta[loc]) for the next E-step, [k*2+t]
+  double bprev[2 * MAXK];  // the values the last executed E-step used (phi of the gamma step)
+};
+
+// Exchange buffer written by peers over NVLink: two epochs' worth of slots.
+struct Xbuf {
+  double val[2][MAXR][2 * MAXK];
+  unsigned long long flag[2][MAXR];
+};
+
+// State of the persistent kernel's fence-free grid barrier (ts_persist.cuh).
+struct PState {
+  // [round parity][word = (hi|lo) * 2K + statistic][0]: monotonic fixed-point accumulators, one per
+  // 1 KB so that the 4K words of a round spread over the L2 slices
+  unsigned long long acc[2][4 * MAXK][128];
+  unsigned long long prev[2][4 * MAXK];        // totals at the end of the previous launch
+  unsigned long long slot[MAXR][2][4 * MAXK][32];  // [source rank][parity][word][0], peer-written, 256 B apart
+  unsigned long long round_ctr;                // rounds run so far (slot tags; same on every rank)
+  uint32_t fault;
+  uint32_t pad;
+};
+
+// Everything a peer GPU writes into lives in one allocation (one IPC handle).
+struct Xchg {
+  Xbuf x;
+  PState ps;
+};
+
+struct Params {
+  const unsigned char *bed;
+  size_t pitch;
+  double *gamma;
+  double *E;
+  uint32_t *cnt;
+  size_t npad;
+  uint32_t n_local;
+  double *lambda;
+  Ctl *ctl;
+  const WorkItem *items;
+  double *partial;  // [grid][2K]
+  uint32_t *rounds; // per item
+  // heldout
+  const unsigned long long *voff;  // CSR over validation loci, local ids
+  const uint32_t *vind;
+  double *ll;  // per validation locus
+  // hyper-parameters
+  double alpha, eta0, eta1, nodetau0, nodekappa, thresh, lscale;
+  uint32_t max_rounds;
+  // exchange
+  int rank, nranks;
+  Xbuf *xlocal;
+  Xbuf *xpeer[MAXR];
+  // persistent kernel
+  PState *pst;
+  PState *pst_peer[MAXR];
+  double fx_scale, fx_inv;  // 2^sh and 2^-sh of the fixed-point statistics
+  int xflush;               // fence.sys after the peer stores (TSGPU_XFLUSH, default on)
+  long long *trace;         // optional phase trace of CTA 0 (TSGPU_TRACE=1), 64 items x 128 slots
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+
+// Persistent-kernel launcher, instantiated per K range in ts_persist_inst.cu (one translation unit
+// per range so that the build parallelises).  Returns cudaErrorInvalidValue for a (K, I) pair that
+// is not instantiated.
+cudaError_t ts_launch_persist(int K, int I, const Params &prm, uint32_t n_items, int grid, int block,
+                              cudaStream_t stream);
+int ts_persist_imax(int K);
+int ts_persist_tmax(int K, int I);

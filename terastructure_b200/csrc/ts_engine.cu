@@ -29,8 +29,7 @@
 #include <string>
 #include <vector>
 
-#include "ts_math.cuh"
-#include "tsgpu.h"
+#include "ts_device.cuh"
 
 // ------------------------------------------------------------------------------------------
 // error plumbing
@@ -56,99 +55,9 @@ static int set_err(int code, const char *fmt, ...) {
   } while (0)
 
 // ------------------------------------------------------------------------------------------
-// device-side structures
-// ------------------------------------------------------------------------------------------
-enum : uint32_t { ITEM_HOL = 1u, ITEM_FIRST = 2u };
-
-struct WorkItem {
-  const unsigned char *col;  // packed column the E-step/gamma step read (bed row or vcol row)
-  uint32_t loc;
-  int32_t vslot;  // index among validation loci, or -1
-  uint32_t flags;
-  uint32_t pad;
-};
-
-constexpr int MAXK = TS_MAX_K;
-constexpr int MAXR = 16;  // ranks in one exchange group
-
-struct Ctl {
-  long long cursor;  // index of the work item being processed
-  uint32_t x;        // rounds completed for the current item
-  uint32_t done;     // round loop finished
-  uint32_t ticket;   // last-CTA-done counter of k_estep
-  uint32_t epoch;    // exchange epoch (multi-GPU)
-  uint32_t fault;    // set when a peer wait timed out
-  uint32_t pad;
-  double bcur[2 * MAXK];   // exp(Elogbeta[loc]) for the next E-step, [k*2+t]
-  double bprev[2 * MAXK];  // the values the last executed E-step used (phi of the gamma step)
-};
-
-// Exchange buffer written by peers over NVLink: two epochs' worth of slots.
-struct Xbuf {
-  double val[2][MAXR][2 * MAXK];
-  unsigned long long flag[2][MAXR];
-};
-
-// State of the persistent kernel's fence-free grid barrier (ts_persist.cuh).
-struct PState {
-  // [round parity][word = (hi|lo) * 2K + statistic][0]: monotonic fixed-point accumulators, one per
-  // 1 KB so that the 4K words of a round spread over the L2 slices
-  unsigned long long acc[2][4 * MAXK][128];
-  unsigned long long prev[2][4 * MAXK];        // totals at the end of the previous launch
-  unsigned long long slot[MAXR][2][4 * MAXK][32];  // [source rank][parity][word][0], peer-written, 256 B apart
-  unsigned long long round_ctr;                // rounds run so far (slot tags; same on every rank)
-  uint32_t fault;
-  uint32_t pad;
-};
-
-// Everything a peer GPU writes into lives in one allocation (one IPC handle).
-struct Xchg {
-  Xbuf x;
-  PState ps;
-};
-
-struct Params {
-  const unsigned char *bed;
-  size_t pitch;
-  double *gamma;
-  double *E;
-  uint32_t *cnt;
-  size_t npad;
-  uint32_t n_local;
-  double *lambda;
-  Ctl *ctl;
-  const WorkItem *items;
-  double *partial;  // [grid][2K]
-  uint32_t *rounds; // per item
-  // heldout
-  const unsigned long long *voff;  // CSR over validation loci, local ids
-  const uint32_t *vind;
-  double *ll;  // per validation locus
-  // hyper-parameters
-  double alpha, eta0, eta1, nodetau0, nodekappa, thresh, lscale;
-  uint32_t max_rounds;
-  // exchange
-  int rank, nranks;
-  Xbuf *xlocal;
-  Xbuf *xpeer[MAXR];
-  // persistent kernel
-  PState *pst;
-  PState *pst_peer[MAXR];
-  double fx_scale, fx_inv;  // 2^sh and 2^-sh of the fixed-point statistics
-  int xflush;               // fence.sys after the peer stores (TSGPU_XFLUSH, default on)
-  long long *trace;         // optional phase trace of CTA 0 (TSGPU_TRACE=1), 64 items x 128 slots
-};
-
-// ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
 constexpr int ESTEP_THREADS = 256;
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 // b[k][t] = exp(psi(lambda[k][t]) - psi(lambda[k][0]+lambda[k][1]))  (estimate_beta, cc:279-296)
 __device__ __forceinline__ void elogbeta_exp(double l0, double l1, double &b0, double &b1) {
@@ -515,8 +424,6 @@ __global__ void k_synth(unsigned char *bed, size_t pitch, uint64_t L, uint32_t n
   }
 }
 
-#include "ts_persist.cuh"
-
 // ------------------------------------------------------------------------------------------
 // host-side engine
 // ------------------------------------------------------------------------------------------
@@ -623,42 +530,8 @@ static void launch_heldout(ts_engine *e, unsigned n_items) {
   }
 }
 
-// persistent-kernel launch (cooperative: every CTA must be resident for the grid barrier)
-template <int K, int I>
-static cudaError_t launch_persist_ki(ts_engine *e, uint32_t n_items) {
-  if constexpr (I > tsp::persist_imax(K)) {
-    return cudaErrorInvalidValue;
-  } else {
-    static bool attr_set[64] = {false};
-    const size_t smem = tsp::persist_smem_bytes(K, I);
-    if (!attr_set[e->cfg.device]) {
-      cudaError_t er = cudaFuncSetAttribute(tsp::k_persist<K, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (er != cudaSuccess) return er;
-      attr_set[e->cfg.device] = true;
-    }
-    void *args[] = {(void *)&e->prm, (void *)&n_items};
-    return cudaLaunchCooperativeKernel((const void *)tsp::k_persist<K, I>, dim3(e->grid_persist),
-                                       dim3(e->block_persist), args, smem, e->stream);
-  }
-}
-template <int K>
-static cudaError_t launch_persist_k(ts_engine *e, uint32_t n_items) {
-  switch (e->ind_per_thread) {
-    case 1: return launch_persist_ki<K, 1>(e, n_items);
-    case 2: return launch_persist_ki<K, 2>(e, n_items);
-    case 3: return launch_persist_ki<K, 3>(e, n_items);
-    case 4: return launch_persist_ki<K, 4>(e, n_items);
-  }
-  return cudaErrorInvalidValue;
-}
 static cudaError_t launch_persist(ts_engine *e, uint32_t n_items) {
-  switch (e->K) {
-#define X(k) \
-  case k: return launch_persist_k<k>(e, n_items);
-    TS_FOR_EACH_K(X)
-#undef X
-  }
-  return cudaErrorInvalidValue;
+  return ts_launch_persist(e->K, e->ind_per_thread, e->prm, n_items, e->grid_persist, e->block_persist, e->stream);
 }
 
 extern "C" {
@@ -768,11 +641,11 @@ int ts_create(const ts_config *cfg, ts_engine **out) {
     int I = 0;
     const char *force = getenv("TSGPU_IPT");  // developer knob: minimum individuals per thread
     const int imin = force ? std::max(1, atoi(force)) : 1;
-    for (int c = imin; c <= tsp::persist_imax(e->K); ++c)
-      if ((uint64_t)e->num_sms * tsp::persist_tmax(e->K, c) * c >= n) { I = c; break; }
+    for (int c = imin; c <= ts_persist_imax(e->K); ++c)
+      if ((uint64_t)e->num_sms * ts_persist_tmax(e->K, c) * c >= n) { I = c; break; }
     if (I == 0) e->staged = true;
     else {
-      const int tmax = tsp::persist_tmax(e->K, I);
+      const int tmax = ts_persist_tmax(e->K, I);
       const uint64_t threads = (n + I - 1) / I;
       e->ind_per_thread = I;
       e->grid_persist = (int)std::min<uint64_t>(e->num_sms, (threads + 63) / 64);  // all SMs once there are 2 warps each

@@ -44,41 +44,3 @@ __device__ __forceinline__ int plink_code(const unsigned char *col, unsigned lon
 __device__ __forceinline__ int code_to_y(int code) { return code - (code >> 1); }
 
 }  // namespace tsm
-
-// ---- table-driven exp(digamma(x)) ---------------------------------------------------------------
-// f(x) = exp(psi(x)) has no cheap closed form (essential singularity at 0, ~x - 1/2 at infinity);
-// it is evaluated from a piecewise degree-12 polynomial table (tools/gen_expsi_table.py: 16
-// sub-intervals per binade on [2^-5, 2^25), max relative error 2.5e-16, one 128-byte row per
-// evaluation) at the cost of 12 FMAs instead of a log, a division, a 7-term series and an exp.
-#define TS_EXPSI_DECL static __device__ __align__(128) const double g_expsi[TS_EXPSI_ROWS * TS_EXPSI_STRIDE]
-#include "ts_expsi_table.inc"
-
-namespace tsm {
-
-__device__ __forceinline__ double exp_digamma_tab(double x) {
-  const int hi = __double2hiint(x);
-  const int e = (hi >> 20) - 1023;  // x > 0 and finite on every call site
-  if (e < TS_EXPSI_EMIN || e > TS_EXPSI_EMAX) return exp(digamma(x));  // out of table: exact slow path
-  const int j = (hi >> 16) & 15;
-  const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(x));  // x * 2^-e
-  const double t = fma(m, 32.0, -(double)(33 + 2 * j));  // 32 * (m - (1 + (2j+1)/32)) in [-1, 1)
-  const double2 *c = reinterpret_cast<const double2 *>(g_expsi + ((e - TS_EXPSI_EMIN) * TS_EXPSI_SUB + j) * TS_EXPSI_STRIDE);
-  const double2 c01 = __ldg(c + 0), c23 = __ldg(c + 1), c45 = __ldg(c + 2), c67 = __ldg(c + 3),
-                c89 = __ldg(c + 4), cab = __ldg(c + 5), ccd = __ldg(c + 6);
-  double p = ccd.x;
-  p = fma(p, t, cab.y);
-  p = fma(p, t, cab.x);
-  p = fma(p, t, c89.y);
-  p = fma(p, t, c89.x);
-  p = fma(p, t, c67.y);
-  p = fma(p, t, c67.x);
-  p = fma(p, t, c45.y);
-  p = fma(p, t, c45.x);
-  p = fma(p, t, c23.y);
-  p = fma(p, t, c23.x);
-  p = fma(p, t, c01.y);
-  p = fma(p, t, c01.x);
-  return p;
-}
-
-}  // namespace tsm

@@ -165,10 +165,10 @@ __device__ __forceinline__ double f_expsi(double x) {
 
 // I individuals per thread live in registers; threads per CTA are capped so that the register
 // file holds them.  Combinations that are not instantiated fall back to the staged path.
-__host__ __device__ constexpr int persist_imax(int K) { return K <= 12 ? 4 : (K <= 20 ? 2 : 1); }
+__host__ __device__ constexpr int persist_imax(int K) { return K <= 20 ? 4 : 1; }
 __host__ __device__ constexpr int persist_tmax(int K, int I) {
   return K <= 12 ? (I == 1 ? 512 : (I == 2 ? 384 : (I == 3 ? 288 : 256)))
-                 : (K <= 20 ? (I == 1 ? 384 : 256) : 256);
+                 : (K <= 20 ? (I == 1 ? 384 : (I == 2 ? 256 : (I == 3 ? 224 : 192))) : 256);
 }
 __host__ __device__ constexpr size_t persist_smem_bytes(int K, int I) {
   return sizeof(double) * (4 * K) + sizeof(long long) * (4 * K * (persist_tmax(K, I) / 32 + 1)) + 16;
