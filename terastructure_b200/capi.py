@@ -83,8 +83,14 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise TsError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                          "or `make -C terastructure_b200/csrc` (there is no fallback path)")
+            # a fresh checkout: build in-tree once (nvcc cross-compiles sm_100a without a GPU)
+            import subprocess
+            try:
+                subprocess.run(["make", "-s", "-j", str(os.cpu_count() or 4), "-C", os.path.join(_HERE, "csrc")],
+                               check=True, stdout=subprocess.DEVNULL)
+            except (OSError, subprocess.CalledProcessError) as ex:
+                raise TsError(f"{LIB_PATH} is not built and building it failed ({ex}); run "
+                              "`make -C terastructure_b200/csrc` (there is no fallback path)")
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in EXPORTS.items():
             fn = getattr(L, name)

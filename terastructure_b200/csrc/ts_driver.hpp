@@ -4,6 +4,8 @@
 // runs on the GPU(s).  Header-only, used by main.cpp.
 #pragma once
 
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <sys/types.h>
 #include <unistd.h>
@@ -126,10 +128,17 @@ struct Env {
 // ---------------------------------------------------------------------------------------------
 struct SNP {
   Env &env;
-  std::vector<uint8_t> rows;  // SNP-major PLINK codes, bytes_per_snp each
+  // SNP-major PLINK codes, bps bytes per locus.  A .bed file is memory-mapped (a 1M x 1M data
+  // set is 250 GB: it is never copied into host RAM as a whole, and never unpacked);
+  // a .012 text file is packed into `owned`.
+  const uint8_t *rows = nullptr;
+  std::vector<uint8_t> owned;
+  void *map_base = nullptr;
+  size_t map_len = 0;
   size_t bps = 0;
   std::vector<std::string> labels;
   explicit SNP(Env &e) : env(e) {}
+  ~SNP() { if (map_base) munmap(map_base, map_len); }
 
   static long count_lines(const std::string &path) {
     FILE *f = fopen(path.c_str(), "r");
@@ -142,9 +151,19 @@ struct SNP {
   }
 
   void count_codes() {  // "missing snps", "0s/1s/2s snps" lines of param.txt (snp.cc:243-247)
+    uint64_t lut[256][4];
+    for (int b = 0; b < 256; ++b) {
+      for (int c = 0; c < 4; ++c) lut[b][c] = 0;
+      for (int j = 0; j < 4; ++j) lut[b][(b >> (2 * j)) & 3]++;
+    }
     uint64_t c[4] = {0, 0, 0, 0};
-    for (uint32_t loc = 0; loc < env.l; ++loc)
-      for (uint32_t i = 0; i < env.n; ++i) c[(rows[loc * bps + (i >> 2)] >> (2 * (i & 3))) & 3]++;
+    const size_t full = env.n / 4, tail = env.n % 4;
+    for (uint32_t loc = 0; loc < env.l; ++loc) {
+      const uint8_t *r = rows + (size_t)loc * bps;
+      for (size_t i = 0; i < full; ++i)
+        for (int k = 0; k < 4; ++k) c[k] += lut[r[i]][k];
+      for (size_t j = 0; j < tail; ++j) c[(r[full] >> (2 * j)) & 3]++;
+    }
     env.plog("missing snps", (uint32_t)c[1]);
     env.plog("0s snps", c[3]);  // the reference counts y=2 under "0s" (snp.cc:207-209)
     env.plog("1s snps", c[2]);
@@ -162,16 +181,20 @@ struct SNP {
     printf("+ fam file tells us %ld individuals\n", n);
     if ((long)env.n != n) { env.lerr("-n input doesn't match individuals in fam file\n"); return -1; }
     bps = (env.n + 3) / 4;
-    FILE *f = fopen(s.c_str(), "rb");
-    if (!f) { env.lerr("cannot open file %s:%s", s.c_str(), strerror(errno)); return -1; }
-    unsigned char h[3] = {0, 0, 0};
-    if (fread(h, 1, 3, f) != 3 || h[0] != 108 || h[1] != 27) { env.lerr("%s magic number incorrect\n", s.c_str()); fclose(f); return -1; }
-    if (h[2] == 0) { env.lerr("individual major mode not supported yet!\n"); fclose(f); return -1; }
-    if (h[2] != 1) { env.lerr("mode problem in %s\n", s.c_str()); fclose(f); return -1; }
-    rows.assign((size_t)env.l * bps, 0);
-    const size_t got = fread(rows.data(), 1, rows.size(), f);
-    fclose(f);
-    if (got != rows.size()) { env.lerr("%s is shorter than -n/-l imply\n", s.c_str()); return -1; }
+    const int fd = open(s.c_str(), O_RDONLY);
+    if (fd < 0) { env.lerr("cannot open file %s:%s", s.c_str(), strerror(errno)); return -1; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 3) { env.lerr("%s magic number incorrect\n", s.c_str()); close(fd); return -1; }
+    map_len = (size_t)st.st_size;
+    map_base = mmap(nullptr, map_len, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (map_base == MAP_FAILED) { map_base = nullptr; env.lerr("cannot map %s:%s", s.c_str(), strerror(errno)); return -1; }
+    const unsigned char *h = (const unsigned char *)map_base;
+    if (h[0] != 108 || h[1] != 27) { env.lerr("%s magic number incorrect\n", s.c_str()); return -1; }
+    if (h[2] == 0) { env.lerr("individual major mode not supported yet!\n"); return -1; }
+    if (h[2] != 1) { env.lerr("mode problem in %s\n", s.c_str()); return -1; }
+    if (map_len - 3 < (size_t)env.l * bps) { env.lerr("%s is shorter than -n/-l imply\n", s.c_str()); return -1; }
+    rows = h + 3;
     count_codes();
     return 0;
   }
@@ -179,7 +202,7 @@ struct SNP {
   int read_012(const std::string &s) {  // snp.cc:6-93: one line of N characters per locus
     printf("+ reading (%d,%d) snps from %s\n", env.n, env.l, s.c_str());
     bps = (env.n + 3) / 4;
-    rows.assign((size_t)env.l * bps, 0);
+    owned.assign((size_t)env.l * bps, 0);
     std::ifstream in(s);
     if (!in) { env.lerr("cannot open file %s:%s", s.c_str(), strerror(errno)); return -1; }
     std::string line;
@@ -189,10 +212,11 @@ struct SNP {
       if (line.size() < env.n) { printf("Error: unexpected lines in file\n"); return -1; }
       for (uint32_t i = 0; i < env.n; ++i) {
         const uint8_t code = (line[i] == '-') ? 1 : code_of_y[(line[i] - '0') % 3];
-        rows[loc * bps + (i >> 2)] |= code << (2 * (i & 3));
+        owned[loc * bps + (i >> 2)] |= code << (2 * (i & 3));
       }
       loc++;
     }
+    rows = owned.data();
     count_codes();
     return 0;
   }
@@ -312,7 +336,7 @@ class SNPSamplingE {
   uint32_t duration() const { return (uint32_t)(time(0) - _start_time); }
 
   void init_heldout_sets() {  // cc:131-140, :196-224
-    TSD_CHECK(ts_sample_validation(_r, _n, _l, _snp.rows.data(), _snp.bps, &_nval, &_val_loc, &_val_off, &_val_indiv));
+    TSD_CHECK(ts_sample_validation(_r, _n, _l, _snp.rows, _snp.bps, &_nval, &_val_loc, &_val_off, &_val_indiv));
     const uint32_t per_loc_h = _n < 2000 ? (_n / 10) : (_n / 100);
     const uint32_t nlocs = (uint32_t)(_l * _env.validation_ratio);
     _env.plog("validation snps per location", per_loc_h);
@@ -342,7 +366,12 @@ class SNPSamplingE {
       _eng.push_back(e);
       _begin.push_back(cfg.n_begin);
       _local.push_back(cfg.n_local);
-      TSD_CHECK(ts_load_bed(e, 0, _l, _snp.rows.data(), _snp.bps));
+      // stream the shard's bytes to the device in chunks of loci (the source may be a mapped file)
+      const uint64_t chunk = std::max<uint64_t>(1, (256ull << 20) / _snp.bps);
+      for (uint64_t lo = 0; lo < _l; lo += chunk) {
+        const uint64_t m = std::min<uint64_t>(chunk, _l - lo);
+        TSD_CHECK(ts_load_bed(e, lo, m, _snp.rows + lo * _snp.bps, _snp.bps));
+      }
       TSD_CHECK(ts_set_validation(e, _nval, _val_loc, _val_off, _val_indiv));
     }
     if (ng > 1) TSD_CHECK(ts_comm_connect_local(_eng.data(), ng));

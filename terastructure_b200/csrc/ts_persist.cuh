@@ -412,18 +412,30 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
                 }
                 if (p.xflush) __threadfence_system();  // push the NVLink writes out now
               }
+              // all ranks' slots are read together (one round trip per sweep), stale ones re-read
               unsigned long long th = 0, tl = 0;
-              for (int r = 0; r < p.nranks && !abort; ++r) {
-                unsigned long long wh, wl;
+              for (int r0 = 0; r0 < p.nranks; r0 += 8) {
+                unsigned long long wh[8], wl[8];
+                unsigned pending = 0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  if (r0 + u < p.nranks) pending |= 1u << u;
                 spins = 0;
-                while (true) {
-                  wh = ld_relaxed_sys(&st->slot[r][par][v][0]);
-                  wl = ld_relaxed_sys(&st->slot[r][par][V + v][0]);
-                  if ((wh & ~FX_MASK) == tag && (wl & ~FX_MASK) == tag) break;
+                while (pending) {
+#pragma unroll
+                  for (int u = 0; u < 8; ++u)
+                    if (pending & (1u << u)) {
+                      wh[u] = ld_relaxed_sys(&st->slot[r0 + u][par][v][0]);
+                      wl[u] = ld_relaxed_sys(&st->slot[r0 + u][par][V + v][0]);
+                    }
+#pragma unroll
+                  for (int u = 0; u < 8; ++u)
+                    if ((pending & (1u << u)) && (wh[u] & ~FX_MASK) == tag && (wl[u] & ~FX_MASK) == tag) pending &= ~(1u << u);
                   if (++spins > SPIN_LIMIT) { abort = true; break; }
                 }
-                th += wh & FX_MASK;
-                tl += wl & FX_MASK;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  if (r0 + u < p.nranks) { th += wh[u] & FX_MASK; tl += wl[u] & FX_MASK; }
               }
               dh = th;
               dl = tl;

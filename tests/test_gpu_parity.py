@@ -360,3 +360,44 @@ def test_exp_digamma_table_on_device():
     o.flush()
     assert rel_err(e.gamma, o.gamma) < 1e-12
     assert rel_err(e.get_lambda(), o.lam) < 1e-12
+
+
+def test_cli_012_input_sigterm_and_gpus(tmp_path):
+    """CLI on a .012 text file (snp.cc:6-93) with missing genotypes, stopped by SIGTERM after a few
+    reports like the reference (main.cc:28-39: save the model, exit 0); `-gpus 2` when two GPUs are
+    visible.  validation.txt rows and gamma_<iter>.txt (-file-suffix) against the reference binary."""
+    import os
+    import signal
+    import subprocess
+    import time
+    import terastructure_b200 as ts
+    from conftest import ROOT
+    c = load_case("synthA")
+    g = c["gold"]
+    y = c["y"]  # [l, n]
+    with open(tmp_path / "d.012", "w") as f:
+        for row in y:
+            f.write("".join("-" if v == 3 else str(int(v)) for v in row) + "\n")
+    exe = os.path.join(ROOT, "terastructure_b200", "bin", "terastructure")
+    ng = 2 if ts.lib().ts_device_count() >= 2 else 1
+    cmd = [exe, "-file", "d.012", "-n", str(c["n"]), "-l", str(c["l"]), "-k", str(c["k"]), "-rfreq", str(c["rfreq"]),
+           "-seed", str(c["seed"]), "-label", "g", "-file-suffix", "-gpus", str(ng)]
+    p = subprocess.Popen(cmd, cwd=tmp_path, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    d = tmp_path / f"n{c['n']}-k{c['k']}-l{c['l']}-g-seed{c['seed']}"
+    vf = d / "validation.txt"
+    t0 = time.time()
+    nrep = len(g["val_iter"])
+    while p.poll() is None and time.time() - t0 < 240:
+        time.sleep(0.2)
+        if vf.exists() and sum(1 for _ in open(vf)) >= nrep:
+            p.send_signal(signal.SIGTERM)
+            break
+    rc = p.wait(timeout=60)
+    assert rc == 0, p.stderr.read()[-2000:]
+    val = np.loadtxt(vf)[:nrep]
+    assert val[:, 0].astype(int).tolist() == g["val_iter"].tolist()
+    assert np.max(np.abs(val[:, 2] - g["val_ll"])) < 6e-10
+    for it in g["val_iter"]:
+        gam = np.loadtxt(d / f"gamma_{it}.txt")
+        ref = g[f"gamma_{it}"]
+        assert np.all(np.abs(gam - ref) <= 1e-6 * np.abs(ref) + 1.01e-8), it
