@@ -116,8 +116,8 @@ class Rng:
         self._h = lib().ts_rng_create(float(seed))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().ts_rng_destroy(self._h)
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.ts_rng_destroy(self._h)
             self._h = None
 
     def get(self):
@@ -179,8 +179,8 @@ class Engine:
         self.nval = 0
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().ts_destroy(self._h)
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.ts_destroy(self._h)
             self._h = _vp()
 
     __del__ = close

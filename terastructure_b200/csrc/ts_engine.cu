@@ -658,7 +658,7 @@ int ts_create(const ts_config *cfg, ts_engine **out) {
     e->prm.fx_scale = ldexp(1.0, sh);
     e->prm.fx_inv = ldexp(1.0, -sh);
     e->prm.trace = nullptr;
-    e->prm.xflush = getenv("TSGPU_XFLUSH") ? atoi(getenv("TSGPU_XFLUSH")) : 1;
+    e->prm.xflush = getenv("TSGPU_XFLUSH") ? atoi(getenv("TSGPU_XFLUSH")) : 0;
     if (getenv("TSGPU_TRACE")) {
       CKE(dalloc(&e->prm.trace, 64 * 128));
       CKE(cudaMemset(e->prm.trace, 0, 64 * 128 * sizeof(long long)));
