@@ -402,6 +402,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
               if (par) { ph1[q] = bh + dh; pl1[q] = bl + dl; } else { ph0[q] = bh + dh; pl0[q] = bl + dl; }
               dh &= FX_MASK;
               dl &= FX_MASK;
+              if (q == 0) TS_TRACE(82 + 2 * x);  // local words complete
             }
             if (p.nranks > 1) {
               const unsigned long long tag = ((rc + 1) & 1023ull) << FX_CNT_SHIFT;
@@ -411,6 +412,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
                   st_relaxed_sys(&p.pst_peer[r]->slot[p.rank][par][V + v][0], tag | dl);
                 }
                 if (p.xflush) __threadfence_system();  // push the NVLink writes out now
+                if (q == 0) TS_TRACE(83 + 2 * x);  // peer stores issued
               }
               // all ranks' slots are read together (one round trip per sweep), stale ones re-read
               unsigned long long th = 0, tl = 0;
