@@ -51,6 +51,20 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic_bytes(iters_per_launch):
+    """DRAM bytes per launch of the persistent kernel from the committed `ncu --set full` capture
+    (profiles/r1_k_persist_ncu_full_metrics.json: one launch of 50 SVI iterations at N=100K, K=10),
+    scaled to this run's launch length.  None when the capture does not apply."""
+    p = os.path.join(ROOT, "profiles", "r1_k_persist_ncu_full_metrics.json")
+    try:
+        m = json.load(open(p))
+        rd = float(m["dram__bytes_read.sum"].split()[0]) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}[m["dram__bytes_read.sum"].split()[1]]
+        wr = float(m["dram__bytes_write.sum"].split()[0]) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}[m["dram__bytes_write.sum"].split()[1]]
+        return (rd + wr) / 50.0 * iters_per_launch
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -321,7 +335,10 @@ def main():
                     "note": "host draws SNP indices with the GSL-exact RNG, ts_steps(host buffer), rounds read back"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": profiled_traffic_bytes(BATCH) if (world == 1 and K == 10 and n_per == N_ONE_GPU) else None,
+                         "traffic_note": "dram__bytes_read+write per launch from profiles/ (ncu --set full), bytes",
+                         "peak_source": peak_src,
                          "kernel": "tsp::k_persist<10> (one cooperative launch per step = BATCH SVI iterations)",
                          "algorithmic_bytes_per_genotype": bpg},
             "wall_s_timed_region": t_wall, "mean_rounds_per_snp": rounds_total / (BATCH * args.steps),

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtsgpu.so")
+LIB_PATH = os.environ.get("TSGPU_LIB") or os.path.join(_HERE, "lib", "libtsgpu.so")  # TSGPU_LIB: A/B builds
 
 TS_MAX_K = 32
 TS_COMM_HANDLE_BYTES = 64
