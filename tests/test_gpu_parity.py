@@ -401,3 +401,27 @@ def test_cli_012_input_sigterm_and_gpus(tmp_path):
         gam = np.loadtxt(d / f"gamma_{it}.txt")
         ref = g[f"gamma_{it}"]
         assert np.all(np.abs(gam - ref) <= 1e-6 * np.abs(ref) + 1.01e-8), it
+
+
+def test_large_shard_falls_back_to_staged_path():
+    """Shards beyond the register-resident kernel's capacity (148 CTAs x 256 threads x 4 individuals
+    at K <= 12) run the staged path automatically; same invariants, no error."""
+    import terastructure_b200 as ts
+    from terastructure_b200 import plink, synth
+    n, l, k = 160_000, 16, 4
+    theta, beta = synth.psd_params(n, l, k, seed=2)
+    e = ts.Engine(n, l, k)
+    e.synth_bed(7, theta, beta, 0.0)
+    g0 = np.random.RandomState(1).gamma(100.0, 0.01, size=(n, k))
+    e.set_gamma(g0)
+    locs = np.array([3, 9, 3], np.uint32)
+    before = e.launch_count
+    rounds = e.steps(locs, want_rounds=True)
+    assert np.all(rounds == 10)
+    assert e.launch_count - before >= 3 * 11          # one launch per round: the staged path
+    for loc in (3, 9):
+        y = plink.unpack(e.get_bed_row(loc)[None, :], n)[0]
+        lam = e.get_lambda(loc, 1)[0]
+        assert abs(lam[:, 0].sum() - k - y.sum()) < 1e-7 * n
+        assert abs(lam[:, 1].sum() - k - (2 - y.astype(np.int64)).sum()) < 1e-7 * n
+    np.testing.assert_array_equal(e.counts, np.full(n, 3, np.uint32))

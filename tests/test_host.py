@@ -124,3 +124,33 @@ def test_argument_validation():
     cfg.k = 3; cfg.n_begin = 2
     assert ts.lib().ts_create(C.byref(cfg), C.byref(h)) == -1
     assert ts.lib().ts_steps(None, None, 0, 0, None) == -1
+
+
+def _cli():
+    exe = os.path.join(ROOT, "terastructure_b200", "bin", "terastructure")
+    assert os.path.exists(exe), "CLI not built (make -C terastructure_b200/csrc)"
+    return exe
+
+
+def test_cli_flags_without_gpu(tmp_path):
+    """The front end keeps the reference's flag handling (src/main.cc:84-187): usage with no
+    arguments (exit -1), -help (exit 0), unknown option -> abort (the reference: assert(0)),
+    -batch prints and exits 0; without a GPU it refuses to run rather than falling back."""
+    import subprocess
+    exe = _cli()
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 255 and "terastructure [OPTIONS]" in r.stdout
+    r = subprocess.run([exe, "-help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "-rfreq" in r.stdout
+    r = subprocess.run([exe, "-n", "5", "-bogus"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode != 0 and "unknown option -bogus" in r.stdout
+    r = subprocess.run([exe, "-batch"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0 and "batch option currently not available" in r.stdout
+    r = subprocess.run([exe, "-file", "x.bed", "-n", "10", "-l", "5", "-k", "2", "-use-test-set"],
+                       capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode != 0 and "-use-test-set" in r.stderr
+    import terastructure_b200 as ts
+    if ts.lib().ts_device_count() == 0:
+        r = subprocess.run([exe, "-file", "x.bed", "-n", "10", "-l", "5", "-k", "2"], capture_output=True, text=True, cwd=tmp_path)
+        assert r.returncode != 0 and "no CPU path" in r.stderr
+        assert not any(p.is_dir() for p in tmp_path.iterdir())  # no output directory was created
