@@ -49,7 +49,7 @@ class SNPSamplingE:
     Multi-GPU: pass this rank's shard (rank, nranks, device) and an `allgather(obj)->list`
     callable; every rank runs the same host loop on the same RNG stream."""
 
-    def __init__(self, env, bed_rows, *, device=0, rank=0, nranks=1, allgather=None, gamma0=None):
+    def __init__(self, env, bed_rows, *, device=0, rank=0, nranks=1, allgather=None, gamma0=None, engine=None):
         self.env = env
         self._n, self._k, self._l = env.n, env.k, env.l
         self._iter = 0
@@ -61,7 +61,10 @@ class SNPSamplingE:
         self._allgather = allgather
         self.validation_rows = []  # (iter, secs, mean LL, count, exp(mean LL)) as validation.txt
         self.stopped = False
-        bed_rows = np.ascontiguousarray(bed_rows, dtype=np.uint8)
+        # engine != None: genotypes are already resident (device-generated synthetic data without
+        # missing entries); bed_rows is then None
+        if bed_rows is not None:
+            bed_rows = np.ascontiguousarray(bed_rows, dtype=np.uint8)
 
         # random number generation (cc:58-63)
         self._r = capi.Rng(env.seed)
@@ -74,10 +77,14 @@ class SNPSamplingE:
         n_begin = min(rank * per, self._n)
         n_local = min(per, self._n - n_begin)
         self.n_begin, self.n_local = n_begin, n_local
-        self.engine = capi.Engine(self._n, self._l, self._k, device=device, rank=rank, nranks=nranks,
-                                  n_begin=n_begin, n_local=n_local,
-                                  online_iterations=env.online_iterations)
-        self.engine.load_bed(bed_rows)
+        if engine is not None:
+            assert engine.n_local == n_local and int(engine.cfg.n_begin) == n_begin
+            self.engine = engine
+        else:
+            self.engine = capi.Engine(self._n, self._l, self._k, device=device, rank=rank, nranks=nranks,
+                                      n_begin=n_begin, n_local=n_local,
+                                      online_iterations=env.online_iterations)
+            self.engine.load_bed(bed_rows)
         self.engine.set_validation(self.val_loc, self.val_off, self.val_indiv)
         if nranks > 1:
             handles = allgather(self.engine.comm_export())
