@@ -636,15 +636,19 @@ int ts_create(const ts_config *cfg, ts_engine **out) {
     const char *path = getenv("TSGPU_PATH");
     e->staged = path && !strcmp(path, "staged");
     // I individuals per thread in registers: the smallest I whose thread cap covers the shard.
-    // Shards too large for the register-resident kernel run the staged path.
+    // Larger shards run the streaming variant of the same kernel (I = 0).
     const uint64_t n = cfg->n_local;
     int I = 0;
     const char *force = getenv("TSGPU_IPT");  // developer knob: minimum individuals per thread
     const int imin = force ? std::max(1, atoi(force)) : 1;
     for (int c = imin; c <= ts_persist_imax(e->K); ++c)
       if ((uint64_t)e->num_sms * ts_persist_tmax(e->K, c) * c >= n) { I = c; break; }
-    if (I == 0) e->staged = true;
-    else {
+    if (I == 0) {
+      // beyond the register-resident capacity: the streaming variant (E read from L2 every round)
+      e->ind_per_thread = 0;
+      e->grid_persist = e->num_sms;
+      e->block_persist = ts_persist_tmax(e->K, 0);
+    } else {
       const int tmax = ts_persist_tmax(e->K, I);
       const uint64_t threads = (n + I - 1) / I;
       e->ind_per_thread = I;

@@ -163,10 +163,12 @@ __device__ __forceinline__ double f_expsi(double x) {
       p.trace[(size_t)i * 128 + (slot)] = clock64();                                          \
   } while (0)
 
-// I individuals per thread live in registers; threads per CTA are capped so that the register
-// file holds them.  Combinations that are not instantiated fall back to the staged path.
+// I >= 1: I individuals per thread live in registers; threads per CTA are capped so that the
+// register file holds them.  I == 0: streaming variant for shards beyond that capacity -- every
+// thread strides over the shard and reads E = exp(psi(gamma)) from global memory (L2) each round.
 __host__ __device__ constexpr int persist_imax(int K) { return K <= 20 ? 4 : 1; }
 __host__ __device__ constexpr int persist_tmax(int K, int I) {
+  if (I == 0) return K <= 12 ? 512 : (K <= 20 ? 384 : 256);  // streaming: E read from L2 every round
   return K <= 12 ? (I == 1 ? 512 : (I == 2 ? 384 : (I == 3 ? 288 : 256)))
                  : (K <= 20 ? (I == 1 ? 384 : (I == 2 ? 256 : (I == 3 ? 224 : 192))) : 256);
 }
@@ -222,30 +224,39 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
   }
   uint32_t prev_loc = 0xffffffffu;
 
-  // this thread's individuals and their E = exp(psi(gamma)) rows, register-resident
-  uint32_t nj[I];
-  bool valid[I];
-  double e[I][K];
+  // this thread's individuals and their E = exp(psi(gamma)) rows, register-resident (I >= 1)
+  constexpr int IR = I > 0 ? I : 1;
+  uint32_t nj[IR];
+  bool valid[IR];
+  double e[IR][K];
+  if constexpr (I > 0) {
 #pragma unroll
-  for (int j = 0; j < I; ++j) {
-    nj[j] = gtid + (uint32_t)j * GT;
-    valid[j] = nj[j] < p.n_local;
+    for (int j = 0; j < I; ++j) {
+      nj[j] = gtid + (uint32_t)j * GT;
+      valid[j] = nj[j] < p.n_local;
 #pragma unroll
-    for (int k = 0; k < K; ++k) e[j][k] = valid[j] ? p.E[(size_t)k * p.npad + nj[j]] : 0.0;
+      for (int k = 0; k < K; ++k) e[j][k] = valid[j] ? p.E[(size_t)k * p.npad + nj[j]] : 0.0;
+    }
   }
   __syncthreads();
 
   for (uint32_t i = 0; i < n_items; ++i) {
     const WorkItem it = p.items[i];
     const unsigned char *col = it.col;
-    int code[I];
+    int code[IR];
+    if constexpr (I > 0) {
 #pragma unroll
-    for (int j = 0; j < I; ++j) code[j] = valid[j] ? tsm::plink_code(col, nj[j]) : 1;
+      for (int j = 0; j < I; ++j) code[j] = valid[j] ? tsm::plink_code(col, nj[j]) : 1;
+    }
     if (i + 1 < n_items) {  // next SNP's genotype column and lambda row -> L2
       const WorkItem nx = p.items[i + 1];
+      if constexpr (I > 0) {
 #pragma unroll
-      for (int j = 0; j < I; ++j)
-        if (valid[j] && (nj[j] & 511) == 0) prefetch_l2(nx.col + (nj[j] >> 2));  // one per 128-byte line
+        for (int j = 0; j < I; ++j)
+          if (valid[j] && (nj[j] & 511) == 0) prefetch_l2(nx.col + (nj[j] >> 2));  // one per 128-byte line
+      } else {
+        for (uint32_t n = gtid * 512u; n < p.n_local; n += GT * 512u) prefetch_l2(nx.col + (n >> 2));
+      }
       if (warp == 0 && lane < V) prefetch_l2(p.lambda + (size_t)nx.loc * V + lane);
     }
     if (warp == 0) {
@@ -275,39 +286,62 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
     TS_TRACE(1);
 
     uint32_t x = 0;
-    double r0[I], r1[I];
+    double r0[IR], r1[IR];
     bool gamma_done = false;
     // ---- gamma natural-gradient step + E refresh (update_gamma/estimate_theta, cc:695-740) ----
     // phi of the LAST E-step: r0/r1 are still in registers, `bl` is the b that E-step used.
-    auto gamma_step = [&](const double *bl) {
+    auto gamma_one = [&](const double *bl, uint32_t n, int y, const double (&en)[K], double q0, double q1, double (&enew)[K]) {
+      const uint32_t cn = p.cnt[n];
+      double g[K];
 #pragma unroll
-      for (int j = 0; j < I; ++j) {
-        if (code[j] == 1) continue;
-        const uint32_t n = nj[j];
-        const uint32_t cn = p.cnt[n];
-        double g[K];
+      for (int k = 0; k < K; ++k) g[k] = p.gamma[(size_t)k * p.npad + n];
+      const double base = p.nodetau0 + (double)cn;
+      const double rho = (p.nodekappa == 0.5) ? rsqrt(base) : pow(base, -p.nodekappa);
+      p.cnt[n] = cn + 1;
 #pragma unroll
-        for (int k = 0; k < K; ++k) g[k] = p.gamma[(size_t)k * p.npad + n];
-        const double base = p.nodetau0 + (double)cn;
-        const double rho = (p.nodekappa == 0.5) ? rsqrt(base) : pow(base, -p.nodekappa);
-        p.cnt[n] = cn + 1;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const double2 bk = *reinterpret_cast<const double2 *>(bl + 2 * k);
-          // y*phimom + (2-y)*phidad = E[k] * (b0[k]*y/s0 + b1[k]*(2-y)/s1)
-          const double w = e[j][k] * fma(bk.x, r0[j], bk.y * r1[j]);
-          const double gn = g[k] + rho * (p.alpha + p.lscale * w - g[k]);
-          p.gamma[(size_t)k * p.npad + n] = gn;
-          e[j][k] = f_expsi(gn);
-        }
+      for (int k = 0; k < K; ++k) {
+        const double2 bk = *reinterpret_cast<const double2 *>(bl + 2 * k);
+        // y*phimom + (2-y)*phidad = E[k] * (b0[k]*y/s0 + b1[k]*(2-y)/s1)
+        const double w = en[k] * fma(bk.x, q0, bk.y * q1);
+        const double gn = g[k] + rho * (p.alpha + p.lscale * w - g[k]);
+        p.gamma[(size_t)k * p.npad + n] = gn;
+        enew[k] = f_expsi(gn);
       }
-      if (i + 1 == n_items) {  // E leaves the registers only at the end of the launch
+      (void)y;
+    };
+    auto gamma_step = [&](const double *bl) {
+      if constexpr (I > 0) {
 #pragma unroll
-        for (int j = 0; j < I; ++j)
-          if (valid[j]) {
+        for (int j = 0; j < I; ++j) {
+          if (code[j] == 1) continue;
+          gamma_one(bl, nj[j], tsm::code_to_y(code[j]), e[j], r0[j], r1[j], e[j]);
+        }
+        if (i + 1 == n_items) {  // E leaves the registers only at the end of the launch
 #pragma unroll
-            for (int k = 0; k < K; ++k) p.E[(size_t)k * p.npad + nj[j]] = e[j][k];
+          for (int j = 0; j < I; ++j)
+            if (valid[j]) {
+#pragma unroll
+              for (int k = 0; k < K; ++k) p.E[(size_t)k * p.npad + nj[j]] = e[j][k];
+            }
+        }
+      } else {
+        for (uint32_t n = gtid; n < p.n_local; n += GT) {
+          const int c = tsm::plink_code(col, n);
+          if (c == 1) continue;
+          const int y = tsm::code_to_y(c);
+          double en[K], s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            en[k] = p.E[(size_t)k * p.npad + n];
+            const double2 bk = *reinterpret_cast<const double2 *>(bl + 2 * k);
+            s0 = fma(en[k], bk.x, s0);
+            s1 = fma(en[k], bk.y, s1);
           }
+          double enew[K];
+          gamma_one(bl, n, y, en, (double)y * fast_rcp(s0), (double)(2 - y) * fast_rcp(s1), enew);
+#pragma unroll
+          for (int k = 0; k < K; ++k) p.E[(size_t)k * p.npad + n] = enew[k];
+        }
       }
     };
     while (true) {
@@ -316,26 +350,37 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
       double vv[V];
 #pragma unroll
       for (int v = 0; v < V; ++v) vv[v] = 0.0;
-#pragma unroll
-      for (int j = 0; j < I; ++j) {
+      auto estep_one = [&](int c, bool ok, const double (&en)[K], double &q0, double &q1) {
         // missing or held out (kv_ok, hh:389-408) -> weight 0; branch-free, the warp stays converged
-        const int y = tsm::code_to_y(code[j]);
-        const double w0 = (code[j] == 1) ? 0.0 : (double)y, w1 = (code[j] == 1) ? 0.0 : (double)(2 - y);
+        const int y = tsm::code_to_y(c);
+        const double w0 = (c == 1) ? 0.0 : (double)y, w1 = (c == 1) ? 0.0 : (double)(2 - y);
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           const double2 bk = *reinterpret_cast<const double2 *>(bx + 2 * k);
-          s0 = fma(e[j][k], bk.x, s0);
-          s1 = fma(e[j][k], bk.y, s1);
+          s0 = fma(en[k], bk.x, s0);
+          s1 = fma(en[k], bk.y, s1);
         }
         // padding threads (no individual) have e = 0, s = 0: keep the reciprocal finite
-        r0[j] = w0 * fast_rcp(valid[j] ? s0 : 1.0);
-        r1[j] = w1 * fast_rcp(valid[j] ? s1 : 1.0);
+        q0 = w0 * fast_rcp(ok ? s0 : 1.0);
+        q1 = w1 * fast_rcp(ok ? s1 : 1.0);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          vv[2 * k] = fma(e[j][k], r0[j], vv[2 * k]);
-          vv[2 * k + 1] = fma(e[j][k], r1[j], vv[2 * k + 1]);
+          vv[2 * k] = fma(en[k], q0, vv[2 * k]);
+          vv[2 * k + 1] = fma(en[k], q1, vv[2 * k + 1]);
         }
+      };
+      if constexpr (I > 0) {
+#pragma unroll
+        for (int j = 0; j < I; ++j) estep_one(code[j], valid[j], e[j], r0[j], r1[j]);
+      } else {
+        for (uint32_t n = gtid; n < p.n_local; n += GT) {
+          double en[K], q0, q1;
+#pragma unroll
+          for (int k = 0; k < K; ++k) en[k] = p.E[(size_t)k * p.npad + n];
+          estep_one(tsm::plink_code(col, n), true, en, q0, q1);
+        }
+        __syncwarp();  // lane-dependent trip count: reconverge before the shuffles
       }
       TS_TRACE(2 + 8 * x + 0);
       // ---- warp: transposed reduction; every warp hands its sums over as fixed point -----------

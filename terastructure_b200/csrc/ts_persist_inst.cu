@@ -10,7 +10,7 @@
 
 template <int K, int I>
 static cudaError_t launch_ki(const Params &prm, uint32_t n_items, int grid, int block, cudaStream_t stream) {
-  if constexpr (I > tsp::persist_imax(K)) {
+  if constexpr (I > tsp::persist_imax(K) && I != 0) {
     return cudaErrorInvalidValue;
   } else {
     const size_t smem = tsp::persist_smem_bytes(K, I);
@@ -33,6 +33,7 @@ static cudaError_t launch_ki(const Params &prm, uint32_t n_items, int grid, int 
 template <int K>
 static cudaError_t launch_k(int I, const Params &prm, uint32_t n_items, int grid, int block, cudaStream_t stream) {
   switch (I) {
+    case 0: return launch_ki<K, 0>(prm, n_items, grid, block, stream);
     case 1: return launch_ki<K, 1>(prm, n_items, grid, block, stream);
     case 2: return launch_ki<K, 2>(prm, n_items, grid, block, stream);
     case 3: return launch_ki<K, 3>(prm, n_items, grid, block, stream);

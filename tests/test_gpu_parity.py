@@ -403,25 +403,35 @@ def test_cli_012_input_sigterm_and_gpus(tmp_path):
         assert np.all(np.abs(gam - ref) <= 1e-6 * np.abs(ref) + 1.01e-8), it
 
 
-def test_large_shard_falls_back_to_staged_path():
-    """Shards beyond the register-resident kernel's capacity (148 CTAs x 256 threads x 4 individuals
-    at K <= 12) run the staged path automatically; same invariants, no error."""
+def test_large_shard_streaming_variant(monkeypatch):
+    """Shards beyond the register-resident capacity (148 CTAs x 256 threads x 4 individuals at
+    K <= 12) run the streaming variant of the persistent kernel (E read from L2 every round):
+    same invariants, and agreement with the staged path on the same inputs."""
     import terastructure_b200 as ts
     from terastructure_b200 import plink, synth
     n, l, k = 160_000, 16, 4
     theta, beta = synth.psd_params(n, l, k, seed=2)
-    e = ts.Engine(n, l, k)
-    e.synth_bed(7, theta, beta, 0.0)
     g0 = np.random.RandomState(1).gamma(100.0, 0.01, size=(n, k))
-    e.set_gamma(g0)
-    locs = np.array([3, 9, 3], np.uint32)
-    before = e.launch_count
-    rounds = e.steps(locs, want_rounds=True)
-    assert np.all(rounds == 10)
-    assert e.launch_count - before >= 3 * 11          # one launch per round: the staged path
-    for loc in (3, 9):
+    locs = np.array([3, 9, 3, 5], np.uint32)
+
+    def run():
+        e = ts.Engine(n, l, k)
+        e.synth_bed(7, theta, beta, 0.01)
+        e.set_gamma(g0)
+        before = e.launch_count
+        rounds = e.steps(locs, want_rounds=True)
+        return e, rounds, e.launch_count - before
+
+    e, rounds, launches = run()
+    assert np.all(rounds == 10) and launches == 1            # one persistent launch for the batch
+    for loc in (3, 9, 5):
         y = plink.unpack(e.get_bed_row(loc)[None, :], n)[0]
+        ok = y != 3
         lam = e.get_lambda(loc, 1)[0]
-        assert abs(lam[:, 0].sum() - k - y.sum()) < 1e-7 * n
-        assert abs(lam[:, 1].sum() - k - (2 - y.astype(np.int64)).sum()) < 1e-7 * n
-    np.testing.assert_array_equal(e.counts, np.full(n, 3, np.uint32))
+        assert abs(lam[:, 0].sum() - k - y[ok].sum()) < 1e-7 * n
+        assert abs(lam[:, 1].sum() - k - (2 - y[ok].astype(np.int64)).sum()) < 1e-7 * n
+    monkeypatch.setenv("TSGPU_PATH", "staged")
+    e2, rounds2, launches2 = run()
+    assert launches2 >= len(locs) * 11                       # one launch per round
+    assert rel_err(e.gamma, e2.gamma) < 1e-11 and rel_err(e.get_lambda(), e2.get_lambda()) < 1e-11
+    np.testing.assert_array_equal(e.counts, e2.counts)
