@@ -56,8 +56,15 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def test_rank_ordered_reduction_gloo():
-    world, port = 2, 29631
+    world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
