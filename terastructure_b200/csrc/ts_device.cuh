@@ -47,7 +47,9 @@ struct PState {
   // 1 KB so that the 4K words of a round spread over the L2 slices
   unsigned long long acc[2][4 * MAXK][128];
   unsigned long long prev[2][4 * MAXK];        // totals at the end of the previous launch
-  unsigned long long slot[MAXR][2][4 * MAXK][32];  // [source rank][parity][word][0], peer-written, 256 B apart
+  // [source rank][parity][statistic][hi|lo]: a GPU's totals are 2K adjacent 16-byte pairs, so the
+  // control warp's stores to a peer (and its polls) coalesce into a few 128-byte NVLink packets
+  unsigned long long slot[MAXR][2][2 * MAXK][2];
   unsigned long long round_ctr;                // rounds run so far (slot tags; same on every rank)
   uint32_t fault;
   uint32_t pad;

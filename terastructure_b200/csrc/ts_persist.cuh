@@ -73,6 +73,15 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// 16-byte (hi, lo) pair in one access: lanes of a warp touch consecutive pairs, so a GPU's totals
+// travel to a peer as a handful of 128-byte packets.  Each word carries its own tag, so a torn pair
+// is harmless.
+__device__ __forceinline__ void st_pair_sys(unsigned long long *p, unsigned long long a, unsigned long long b) {
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_pair_sys(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void red_add(unsigned long long *p, unsigned long long v) {
   asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -452,10 +461,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
             if (p.nranks > 1) {
               const unsigned long long tag = ((rc + 1) & 1023ull) << FX_CNT_SHIFT;
               if (blockIdx.x == 0) {
-                for (int r = 0; r < p.nranks; ++r) {
-                  st_relaxed_sys(&p.pst_peer[r]->slot[p.rank][par][v][0], tag | dh);
-                  st_relaxed_sys(&p.pst_peer[r]->slot[p.rank][par][V + v][0], tag | dl);
-                }
+                for (int r = 0; r < p.nranks; ++r) st_pair_sys(&p.pst_peer[r]->slot[p.rank][par][v][0], tag | dh, tag | dl);
                 if (p.xflush) __threadfence_system();  // push the NVLink writes out now
                 if (q == 0) TS_TRACE(83 + 2 * x);  // peer stores issued
               }
@@ -471,10 +477,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
                 while (pending) {
 #pragma unroll
                   for (int u = 0; u < 8; ++u)
-                    if (pending & (1u << u)) {
-                      wh[u] = ld_relaxed_sys(&st->slot[r0 + u][par][v][0]);
-                      wl[u] = ld_relaxed_sys(&st->slot[r0 + u][par][V + v][0]);
-                    }
+                    if (pending & (1u << u)) ld_pair_sys(&st->slot[r0 + u][par][v][0], wh[u], wl[u]);
 #pragma unroll
                   for (int u = 0; u < 8; ++u)
                     if ((pending & (1u << u)) && (wh[u] & ~FX_MASK) == tag && (wl[u] & ~FX_MASK) == tag) pending &= ~(1u << u);
