@@ -457,3 +457,52 @@ def test_run_to_run_determinism():
         e.close()
     for a, b in zip(*outs):
         np.testing.assert_array_equal(a, b)
+
+
+def test_invariants_at_full_bench_size():
+    """BASELINE configs[2] at full size: 100 000 individuals x 1 000 000 SNPs, K = 10 (25 GB packed,
+    generated on the device, validation set of 5 000 loci x 1 000 individuals sampled with the exact
+    RNG stream).  The oracle cannot run this; check size-independent properties after 300 SVI
+    iterations that include visits to validation loci:
+      sum_k lambda[loc][k][0] - K*eta0 = sum over non-held-out n of y[n], same for (2 - y);
+      step counts = visits minus held-out visits;  gamma row sums follow the rho recurrence."""
+    import terastructure_b200 as ts
+    from terastructure_b200 import plink, synth
+    n, l, k = 100_000, 1_000_000, 10
+    _, beta = synth.psd_params(1, l, k, seed=1)
+    theta = np.random.RandomState(1001).dirichlet(np.full(k, 0.1), size=n)
+    e = ts.Engine(n, l, k)
+    e.synth_bed(1, theta, beta, 0.0)
+    rng = ts.Rng(1234)
+    vl, vo, vi = rng.sample_validation(n, l, None)
+    assert len(vl) == 5000 and np.all(np.diff(vo) == 1000)
+    e.set_validation(vl, vo, vi)
+    g0 = rng.init_gamma(n, k)
+    e.set_gamma(g0)
+    locs = rng.sample_locs(l, 300)
+    locs[[7, 150]] = vl[[11, 4000]]          # force two training visits to validation loci
+    rounds = e.steps(locs, want_rounds=True)
+    assert np.all(rounds == 10)
+    cnt = np.zeros(n, np.int64)
+    rowsum = g0.sum(1)
+    slot = {int(v): j for j, v in enumerate(vl)}   # ~1.5 of 300 random loci are validation loci anyway
+    held = {int(x): vi[vo[slot[int(x)]]:vo[slot[int(x)] + 1]] for x in locs if int(x) in slot}
+    for loc in locs:
+        ok = np.ones(n, bool)
+        if int(loc) in held:
+            ok[held[int(loc)]] = False
+        rho = (2.0 + cnt) ** -0.5
+        rowsum = np.where(ok, (1 - rho) * rowsum + rho * (1.0 + 2.0 * l), rowsum)
+        cnt += ok
+    np.testing.assert_array_equal(e.counts, cnt)
+    np.testing.assert_allclose(e.gamma.sum(1), rowsum, rtol=1e-12)
+    for loc in (int(locs[0]), int(vl[11]), int(locs[-1])):
+        y = plink.unpack(e.get_bed_row(loc)[None, :], n)[0].astype(np.int64)
+        ok = np.ones(n, bool)
+        if loc in held:
+            ok[held[loc]] = False
+        lam = e.get_lambda(loc, 1)[0]
+        assert abs(lam[:, 0].sum() - k - y[ok].sum()) < 1e-7 * n
+        assert abs(lam[:, 1].sum() - k - (2 - y[ok]).sum()) < 1e-7 * n
+    s, c, per = e.heldout_ll(first=True)      # 5 * 10^6 held-out genotypes at Ebeta = 1/2
+    assert c == 5_000_000 and np.isfinite(s) and -2.0 < s / c < -0.5

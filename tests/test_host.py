@@ -154,3 +154,17 @@ def test_cli_flags_without_gpu(tmp_path):
         r = subprocess.run([exe, "-file", "x.bed", "-n", "10", "-l", "5", "-k", "2"], capture_output=True, text=True, cwd=tmp_path)
         assert r.returncode != 0 and "no CPU path" in r.stderr
         assert not any(p.is_dir() for p in tmp_path.iterdir())  # no output directory was created
+
+
+def test_ziggurat_tables_are_reproducible(tmp_path):
+    """The GSL-exact Gaussian ziggurat tables (product copy and oracle-shim copy) are regenerated from
+    first principles by tools/gen_zig_tables.py: the committed files must equal a fresh run."""
+    import subprocess
+    import sys
+    pytest.importorskip("mpmath")
+    gen = os.path.join(ROOT, "tools", "gen_zig_tables.py")
+    for committed, prefix in ((os.path.join(ROOT, "terastructure_b200", "csrc", "zig_tables.inc"), "tszig"),
+                              (os.path.join(ROOT, "oracle", "gsl_shim", "zig_tables.h"), "zig")):
+        out = tmp_path / os.path.basename(committed)
+        subprocess.run([sys.executable, gen, str(out), prefix], check=True, stdout=subprocess.DEVNULL)
+        assert open(out).read() == open(committed).read()
