@@ -74,7 +74,8 @@ int ts_device_count(void);
 /* Replaces the allocation part of the SNPSamplingE ctor (snpsamplinge.cc:6-37) and
  * start_threads (snpsamplinge.cc:252-265): allocates the device-resident state
  * (2-bit packed genotype shard, gamma, exp(psi(gamma)), per-individual step counts,
- * lambda) and the stream/graphs that replace the PhiRunnerE pool.  lambda is set to eta
+ * lambda) and the stream on which the persistent cooperative kernel that replaces the PhiRunnerE
+ * pool is launched.  lambda is set to eta
  * (init_lambda, snpsamplinge.cc:239-250). */
 int ts_create(const ts_config *cfg, ts_engine **out);
 /* The reference never frees (infer() exits the process); we do. */
