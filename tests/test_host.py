@@ -168,3 +168,60 @@ def test_ziggurat_tables_are_reproducible(tmp_path):
         out = tmp_path / os.path.basename(committed)
         subprocess.run([sys.executable, gen, str(out), prefix], check=True, stdout=subprocess.DEVNULL)
         assert open(out).read() == open(committed).read()
+
+
+class _OracleEngine:
+    """Stand-in for capi.Engine backed by the CPU oracle: lets the host-side driver logic of
+    SNPSamplingE (report cadence, _iter bookkeeping, stopping rule, RNG pre-draws) run without a
+    GPU.  Test infrastructure only."""
+
+    def __init__(self, case):
+        self.o = ol.Oracle(case["y"], case["k"], case["seed"])
+        self.n_local, self.nval = case["n"], 0
+
+        class _Cfg:
+            n_begin = 0
+        self.cfg = _Cfg()
+
+    def set_validation(self, vl, vo, vi):
+        ovl, _, ovi = self.o.validation()
+        np.testing.assert_array_equal(vl, ovl)
+        np.testing.assert_array_equal(vi, ovi)
+        self.nval = len(vl)
+
+    def set_gamma(self, g):
+        np.testing.assert_array_equal(g, self.o.gamma)
+
+    def steps(self, locs, hol_mode=False, want_rounds=False):
+        for loc in locs:
+            self.o.train_loc(int(loc))
+
+    def heldout_ll(self, first=False):
+        _, a, cnt, per = self.o.heldout(first=first, per_locus=True)
+        return float(per.sum()), cnt, per
+
+    def sync(self):
+        pass
+
+    gamma = property(lambda s: (s.o.flush(), s.o.gamma)[1])
+    theta = property(lambda s: (s.o.flush(), s.o.theta)[1])
+
+
+def test_driver_host_logic_against_golden(fixture_case, tmp_path):
+    """SNPSamplingE's host loop (Python mirror of snpsamplinge.cc:417-544) on top of the oracle:
+    same report iterations, counts and stop (9050) as the reference binary, validation.txt and
+    theta.txt written in the reference's formats."""
+    import terastructure_b200 as ts
+    c = fixture_case
+    g = c["gold"]
+    env = ts.Env(c["n"], c["k"], c["l"], seed=c["seed"], rfreq=c["rfreq"], outdir=str(tmp_path))
+    s = ts.SNPSamplingE(env, None, engine=_OracleEngine(c))
+    s.infer()
+    assert s.stopped and s._iter == 9050
+    assert [r[0] for r in s.validation_rows] == g["val_iter"].tolist()
+    assert [r[3] for r in s.validation_rows] == g["val_count"].tolist()
+    np.testing.assert_allclose([r[2] for r in s.validation_rows], g["val_ll"], atol=6e-10, rtol=0)
+    val = np.loadtxt(tmp_path / "validation.txt")
+    assert val.shape == (10, 5) and val[:, 0].astype(int).tolist() == g["val_iter"].tolist()
+    import hashlib
+    assert hashlib.md5(open(tmp_path / "theta.txt", "rb").read()).hexdigest() == "ae1136d8769318e9840b1f7dd1d1ac53"
