@@ -1022,7 +1022,7 @@ int ts_sync(ts_engine *e) {
   if (!e) return set_err(TS_ERR_ARG, "ts_sync: null engine");
   if (use_device(e)) return TS_ERR_CUDA;
   CK(cudaStreamSynchronize(e->stream));
-  return TS_OK;
+  return check_fault(e);  // asynchronous ts_steps batches report a lost CTA / rank here
 }
 
 // ---- exchange -------------------------------------------------------------------------------
