@@ -15,10 +15,12 @@ def pytest_configure(config):
 
 
 def load_fixture_rows():
-    """The reference's bundled data set (data/test.bed): packed rows [10000, 50]."""
-    raw = open(os.path.join(GOLDEN, "fixture_n200_l10000.bed"), "rb").read()
-    assert raw[:3] == b"\x6c\x1b\x01"
-    return np.frombuffer(raw[3:], dtype=np.uint8).reshape(10000, 50).copy()
+    """The reference's bundled data set (data/test.bed, N=200 x L=10000): PLINK-packed rows [10000, 50].
+    Stored as a compressed array (tools/make_golden.py) rather than as a copy of the .bed file."""
+    z = np.load(os.path.join(GOLDEN, "fixture_genotypes.npz"))
+    rows = z["rows"]
+    assert rows.shape == (10000, 50) and rows.dtype == np.uint8
+    return rows.copy()
 
 
 def load_case(name):

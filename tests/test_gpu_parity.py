@@ -293,7 +293,8 @@ def test_cli_drop_in(tmp_path):
     exe = os.path.join(ROOT, "terastructure_b200", "bin", "terastructure")
     assert os.path.exists(exe), "CLI not built"
     g = np.load(os.path.join(GOLDEN, "fixture.npz"))
-    rows = np.frombuffer(open(os.path.join(GOLDEN, "fixture_n200_l10000.bed"), "rb").read()[3:], np.uint8).reshape(10000, 50)
+    from conftest import load_fixture_rows
+    rows = load_fixture_rows()
     plink.write_bed(str(tmp_path / "test"), rows, 200)
     r = subprocess.run([exe, "-file", "test.bed", "-n", "200", "-l", "10000", "-k", "3", "-stochastic", "-nthreads", "1",
                         "-rfreq", "1000", "-seed", "1234", "-label", "test"], cwd=tmp_path, capture_output=True, text=True,
