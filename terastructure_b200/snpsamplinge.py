@@ -132,8 +132,8 @@ class SNPSamplingE:
         if not first:
             self._iter += len(self.val_loc)  # snp_likelihood: _iter++ per locus (hh:333)
         s, k = self._reduce_ll(per, cnt)
-        a = s / k
-        self.validation_rows.append((self._iter, self.duration(), a, k, math.exp(a)))
+        a = s / k if k else float("nan")  # the reference divides 0.0/0 here (N < 10): NaN, no stop
+        self.validation_rows.append((self._iter, self.duration(), a, k, math.exp(a) if a == a else a))
         if self.env.outdir and self.rank == 0:
             with open(os.path.join(self.env.outdir, "validation.txt"), "a") as f:
                 f.write("%d\t%d\t%.9f\t%d\t%f\n" % self.validation_rows[-1])
