@@ -135,7 +135,11 @@ __device__ __forceinline__ double exp_neg(double r) {
 __device__ __forceinline__ double f_expsi(double x) {
   const bool small = x < 8.0;
   const double xs = small ? x + 8.0 : x;
-  const double u = fast_rcp(xs);
+  // u = 1/xs enters f only through the correction u*q(u) <= f/1500, so ONE Newton step on the
+  // 20-bit seed (relative error < 1e-11) moves f by less than 1e-14 relative
+  double u;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(u) : "d"(xs));
+  u = fma(u, fma(-xs, u, 1.0), u);
   // q(u) = g2 + g3 u + ... + g16 u^14, Estrin (dependent DFMA latency on B200 is ~23 cycles)
   const double u2 = u * u;
   const double a0 = fma(0x1.5555555555555p-6, u, 0x1.5555555555555p-5);
@@ -182,7 +186,7 @@ __host__ __device__ constexpr int persist_tmax(int K, int I) {
                  : (K <= 20 ? (I == 1 ? 384 : (I == 2 ? 256 : (I == 3 ? 224 : 192))) : 256);
 }
 __host__ __device__ constexpr size_t persist_smem_bytes(int K, int I) {
-  return sizeof(double) * (4 * K) + sizeof(long long) * (4 * K * (persist_tmax(K, I) / 32 + 1)) + 16;
+  return sizeof(double) * (8 * K) + sizeof(long long) * (4 * K * (persist_tmax(K, I) / 32 + 1)) + 16;
 }
 
 template <int K, int I>
@@ -192,14 +196,18 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
   constexpr int VPL = (V + 31) / 32;  // statistics per lane of the control warp
   constexpr int WS = persist_tmax(K, I) / 32 + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *s_b = reinterpret_cast<double *>(smem_raw);                // [2][V]: b of round x at [x&1]
-  long long *s_fix = reinterpret_cast<long long *>(s_b + 2 * V);     // [NW][WS] per-warp fixed-point words
+  double *s_b = reinterpret_cast<double *>(smem_raw);                // [2][V]: b of round x >= 1 at [x&1]
+  double *s_b0 = s_b + 2 * V;                                        // [2][V]: b of round 0 of SNP i at [i&1]
+  long long *s_fix = reinterpret_cast<long long *>(s_b0 + 2 * V);    // [NW][WS] per-warp fixed-point words
   int *s_flag = reinterpret_cast<int *>(s_fix + NW * WS);  // bit 0: round loop done, bit 1: abort
 
   PState *st = p.pst;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
   const uint32_t GT = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
   const unsigned long long G = gridDim.x;
+  const double fx_hi_off = -4503599627370496.0 * p.fx_inv, fx_lo_inv = p.fx_inv * (1.0 / FX_LO_SCALE),
+               fx_lo_off = -4503599627370496.0 * fx_lo_inv;  // powers of two: exact
+  const double big_thr = 2.0 * V * p.thresh;  // one |delta lambda| this large rules convergence out
 
   // which statistic this lane ends up holding after tr_reduce
   // (tr_level splits a NOMINAL count that is the same for every lane; a lane that took a short
@@ -268,13 +276,15 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
       }
       if (warp == 0 && lane < V) prefetch_l2(p.lambda + (size_t)nx.loc * V + lane);
     }
-    if (warp == 0) {
+    // b of round 0 comes from the stored lambda row (estimate_beta, cc:279-296).  A helper warp
+    // prepared it while the previous SNP's gamma step ran, unless this is the launch's first SNP or
+    // the same locus again (its row was not final then): the control warp does it here in that case.
+    auto b_from_row = [&](uint32_t loc, double *dst) {
       double own[VPL];
 #pragma unroll
       for (int q = 0; q < VPL; ++q) {
         const int v = lane + 32 * q;
-        if (it.loc != prev_loc) lam[q] = (v < V) ? __ldcg(p.lambda + (size_t)it.loc * V + v) : 1024.0;
-        own[q] = lam[q];
+        own[q] = (v < V) ? __ldcg(p.lambda + (size_t)loc * V + v) : 1024.0;
       }
 #pragma unroll
       for (int q = 0; q < VPL; ++q) {
@@ -285,10 +295,42 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
         s += l0;
         s += l1;
         const double b = f_expsi(own[q]) * fast_rcp(f_expsi(s));
-        if (v < V) s_b[v] = b;
+        if (v < V) dst[v] = b;
+      }
+    };
+    const bool prepared = i > 0 && it.loc != prev_loc;
+    double *b_first = s_b0 + (i & 1) * V;
+    if (warp == 0) {
+      if (it.loc != prev_loc) {
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+          const int v = lane + 32 * q;
+          lam[q] = (v < V) ? __ldcg(p.lambda + (size_t)it.loc * V + v) : 1024.0;
+        }
+      }
+      if (!prepared) {
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+          const int v = lane + 32 * q;
+          const double other = __shfl_xor_sync(0xffffffffu, lam[q], 1);
+          const double l0 = (v & 1) ? other : lam[q], l1 = (v & 1) ? lam[q] : other;
+          double s = 0.0;
+          s += l0;
+          s += l1;
+          const double b = f_expsi(lam[q]) * fast_rcp(f_expsi(s));
+          if (v < V) b_first[v] = b;
+        }
       }
       if (lane == 0) *s_flag = 0;
     }
+    // the helper's job for the NEXT SNP; called once per SNP by warp W-1, before its gamma step
+    auto prepare_next = [&]() {
+      if (warp == W - 1 && i + 1 < n_items) {
+        const uint32_t nloc = p.items[i + 1].loc;
+        if (nloc != it.loc) b_from_row(nloc, s_b0 + ((i + 1) & 1) * V);
+        __syncwarp();
+      }
+    };
     prev_loc = it.loc;
     TS_TRACE(0);
     __syncthreads();
@@ -354,7 +396,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
       }
     };
     while (true) {
-      const double *bx = s_b + (x & 1) * V;
+      const double *bx = x == 0 ? b_first : s_b + (x & 1) * V;
       // ---- E-step over this thread's individuals: registers + broadcast shared-memory b --------
       double vv[V];
 #pragma unroll
@@ -428,6 +470,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
       // so when this round is known to be the last one the gamma step runs now, in the shadow of
       // the grid barrier, and the control warp collects the totals afterwards.
       if (x + 1 >= p.max_rounds && !(it.flags & ITEM_HOL)) {
+        prepare_next();
         gamma_step(bx);
         gamma_done = true;
       }
@@ -487,14 +530,17 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
                 for (int u = 0; u < 8; ++u)
                   if (r0 + u < p.nranks) { th += wh[u] & FX_MASK; tl += wl[u] & FX_MASK; }
               }
-              dh = th;
-              dl = tl;
+              // every GPU's low word is below 148 * 2^44, but the sum over ranks can pass 2^52, the
+              // limit of the mantissa conversion below: move the carry into the high word (exact)
+              dh = th + (tl >> 44);
+              dl = tl & ((1ull << 44) - 1);
             }
           }
-          // u64 -> double through the mantissa (both < 2^52): one integer OR and one DADD each
-          const double dhd = __longlong_as_double((long long)(dh | 0x4330000000000000ull)) - 4503599627370496.0;
-          const double dld = __longlong_as_double((long long)(dl | 0x4330000000000000ull)) - 4503599627370496.0;
-          tot[q] = fma(dld, 1.0 / FX_LO_SCALE, dhd) * p.fx_inv;
+          // u64 -> double through the mantissa (both < 2^52): (2^52 + d) * 2^-s - 2^(52-s) is exact,
+          // so each word costs one integer OR and one DFMA; the sum of the two rounds once
+          const double dhd = fma(__longlong_as_double((long long)(dh | 0x4330000000000000ull)), p.fx_inv, fx_hi_off);
+          const double dld = fma(__longlong_as_double((long long)(dl | 0x4330000000000000ull)), fx_lo_inv, fx_lo_off);
+          tot[q] = dhd + dld;
         }
         TS_TRACE(2 + 8 * x + 4);
         // new lambda -> new b first (the critical path of the round); convergence test afterwards
@@ -506,22 +552,38 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
           oldlam[q] = lam[q];
           own[q] = (v < V) ? ((v & 1) ? p.eta1 : p.eta0) + tot[q] : 1024.0;  // update_lambda (cc:267-277); idle lanes: any large value
           lam[q] = own[q];
-          const double fo = f_expsi(own[q]);
-          const double other = __shfl_xor_sync(0xffffffffu, own[q], 1);
-          const double l0 = (v & 1) ? other : own[q], l1 = (v & 1) ? own[q] : other;
-          double s = 0.0;
-          s += l0;
-          s += l1;
-          const double b = fo * fast_rcp(f_expsi(s));  // estimate_beta (cc:279-296)
-          if (v < V) bn[v] = b;
+          if (x + 1 < p.max_rounds) {  // the last permitted round has no successor that would read b
+            const double fo = f_expsi(own[q]);
+            const double other = __shfl_xor_sync(0xffffffffu, own[q], 1);
+            const double l0 = (v & 1) ? other : own[q], l1 = (v & 1) ? own[q] : other;
+            double s = 0.0;
+            s += l0;
+            s += l1;
+            const double b = fo * fast_rcp(f_expsi(s));  // estimate_beta (cc:279-296)
+            if (v < V) bn[v] = b;
+          }
         }
-        double chg = 0.0;
+        // Convergence (cc:359-365): mean |delta lambda| < thresh.  The sum needs five dependent
+        // 64-bit shuffle levels and a division on the round's critical path, so it is only formed
+        // when it can matter: not in the last permitted round (done regardless), and not when one
+        // statistic alone moved by 2*V*thresh or more (the mean is then >= thresh whatever the
+        // rounding) -- both decided by one warp vote.
+        const bool last = x + 1 >= p.max_rounds;
+        bool big = false;
 #pragma unroll
         for (int q = 0; q < VPL; ++q)
-          if (lane + 32 * q < V) chg += fabs(own[q] - oldlam[q]);
-        chg = warp_sum(chg);
+          if (lane + 32 * q < V) big |= fabs(own[q] - oldlam[q]) >= big_thr;
+        big = __any_sync(0xffffffffu, big);
         abort = __any_sync(0xffffffffu, abort);
-        const bool done = (chg / (double)V < p.thresh) || (x + 1 >= p.max_rounds);  // cc:359-365
+        bool done = last;
+        if (!last && !big) {
+          double chg = 0.0;
+#pragma unroll
+          for (int q = 0; q < VPL; ++q)
+            if (lane + 32 * q < V) chg += fabs(own[q] - oldlam[q]);
+          chg = warp_sum(chg);
+          done = chg / (double)V < p.thresh;
+        }
         if (done && blockIdx.x == 0) {
 #pragma unroll
           for (int q = 0; q < VPL; ++q)
@@ -545,7 +607,10 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
 
     // early-converged SNPs take the gamma step here; the usual case (all rounds run) took it
     // inside the last round, in the shadow of that round's grid barrier
-    if (!gamma_done && !(it.flags & ITEM_HOL)) gamma_step(s_b + ((x - 1) & 1) * V);
+    if (!gamma_done) {
+      prepare_next();
+      if (!(it.flags & ITEM_HOL)) gamma_step(x == 1 ? b_first : s_b + ((x - 1) & 1) * V);
+    }
     TS_TRACE(100);
     __syncthreads();  // s_b is rewritten for the next SNP
     TS_TRACE(101);
