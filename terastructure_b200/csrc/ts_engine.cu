@@ -641,8 +641,21 @@ int ts_create(const ts_config *cfg, ts_engine **out) {
     int I = 0;
     const char *force = getenv("TSGPU_IPT");  // developer knob: minimum individuals per thread
     const int imin = force ? std::max(1, atoi(force)) : 1;
-    for (int c = imin; c <= ts_persist_imax(e->K); ++c)
-      if ((uint64_t)e->num_sms * ts_persist_tmax(e->K, c) * c >= n) { I = c; break; }
+    // Among the I that fit, take the one with the fewest warps on the busiest of the SM's four
+    // schedulers (the warp-level reduction and the CTA sum are issue-bound per scheduler), not going
+    // below two; ties go to the smaller I (shorter dependent FP64 chains, fewer registers).
+    // B200, K = 10, us per SVI iteration: 60K individuals I=1/13 warps 30.9, I=2/7 warps 28.3;
+    // 80K I=2/9 warps 30.9, I=3/6 warps 28.9; 100K I=2/11 warps 31.2, I=3/8 warps 29.7, I=4/6 warps 32.5.
+    int best = 1 << 30;
+    for (int c = imin; c <= ts_persist_imax(e->K); ++c) {
+      if ((uint64_t)e->num_sms * ts_persist_tmax(e->K, c) * c < n) continue;
+      if (force) { I = c; break; }  // the knob pins the first I >= its value that fits
+      const uint64_t threads = (n + c - 1) / c;
+      const uint64_t grid = std::min<uint64_t>(e->num_sms, (threads + 63) / 64);
+      const int warps = (int)(((threads + grid - 1) / grid + 31) / 32);
+      const int score = std::max((warps + 3) / 4, 2);
+      if (score < best) { best = score; I = c; }
+    }
     if (I == 0) {
       // beyond the register-resident capacity: the streaming variant (E read from L2 every round)
       e->ind_per_thread = 0;

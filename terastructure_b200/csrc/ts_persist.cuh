@@ -182,7 +182,10 @@ __device__ __forceinline__ double f_expsi(double x) {
 __host__ __device__ constexpr int persist_imax(int K) { return K <= 20 ? 4 : 1; }
 __host__ __device__ constexpr int persist_tmax(int K, int I) {
   if (I == 0) return K <= 12 ? 512 : (K <= 20 ? 384 : 256);  // streaming: E read from L2 every round
-  return K <= 12 ? (I == 1 ? 512 : (I == 2 ? 384 : (I == 3 ? 288 : 256)))
+#ifndef TS_I3_TMAX
+#define TS_I3_TMAX 256  // registers are allocated per 4 warps: 288 threads would cap at 168 registers like 384 do (spills)
+#endif
+  return K <= 12 ? (I == 1 ? 512 : (I == 2 ? 384 : (I == 3 ? TS_I3_TMAX : 256)))
                  : (K <= 20 ? (I == 1 ? 384 : (I == 2 ? 256 : (I == 3 ? 224 : 192))) : 256);
 }
 __host__ __device__ constexpr size_t persist_smem_bytes(int K, int I) {
