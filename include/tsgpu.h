@@ -162,6 +162,13 @@ int ts_comm_export(ts_engine *e, void *handle_out);
 int ts_comm_connect(ts_engine *e, const void *all_handles /* nranks x 64 bytes, rank order */);
 int ts_comm_connect_local(ts_engine **engines, int n);
 
+/* Launch geometry the engine uses for a shard of n_local individuals on a device with num_sms SMs
+ * (pure host arithmetic, no device needed): individuals per thread held in registers by the
+ * persistent kernel (0 = streaming variant for shards beyond the register-resident capacity),
+ * CTAs and threads per CTA.  The reference's counterpart is the static split of individuals over
+ * `-nthreads` workers (split_all_indivs, snpsamplinge.cc:298-318). */
+int ts_plan_shard(uint64_t n_local, int k, int num_sms, int *ind_per_thread, int *grid, int *block);
+
 /* ---- profiling hooks ------------------------------------------------------------------- */
 /* Kernels launched by this engine since creation (for bench.py's gpu_launches). */
 uint64_t ts_launch_count(const ts_engine *e);

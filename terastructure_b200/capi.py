@@ -59,6 +59,7 @@ EXPORTS = {
     "ts_comm_export": (_i, [_vp, _vp]),
     "ts_comm_connect": (_i, [_vp, _vp]),
     "ts_comm_connect_local": (_i, [C.POINTER(_vp), _i]),
+    "ts_plan_shard": (_i, [_u64, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "ts_launch_count": (_u64, [_vp]),
     "ts_timer_start": (_i, [_vp]),
     "ts_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
@@ -302,3 +303,11 @@ class Engine:
 def connect_local(engines):
     arr = (_vp * len(engines))(*[e._h for e in engines])
     check(lib().ts_comm_connect_local(arr, len(engines)))
+
+
+def plan_shard(n_local, k, num_sms=148):
+    """(individuals per thread, CTAs, threads per CTA) the engine uses for a shard of `n_local`
+    individuals; individuals per thread 0 = streaming variant.  Host arithmetic only."""
+    ipt, grid, block = C.c_int(), C.c_int(), C.c_int()
+    check(lib().ts_plan_shard(n_local, k, num_sms, C.byref(ipt), C.byref(grid), C.byref(block)))
+    return ipt.value, grid.value, block.value

@@ -567,6 +567,44 @@ void ts_config_defaults(ts_config *cfg, uint64_t n, uint64_t l, uint32_t k) {
   cfg->nranks = 1;
 }
 
+// Launch geometry of the persistent kernel for a shard of n individuals.
+// I individuals per thread live in registers; among the I that fit, take the one with the fewest
+// warps on the busiest of the SM's four schedulers (the warp-level reduction and the CTA sum are
+// issue-bound per scheduler), not going below two; ties go to the smaller I (shorter dependent
+// FP64 chains, fewer registers).  Shards beyond the register-resident capacity run the streaming
+// variant (I = 0: E read from L2 every round).
+// B200, K = 10, us per SVI iteration: 60K individuals I=1/13 warps 30.9, I=2/7 warps 28.3;
+// 80K I=2/9 warps 30.9, I=3/6 warps 28.9; 100K I=2/11 warps 31.2, I=3/8 warps 29.7, I=4/6 warps 32.5.
+static void plan_shard(uint64_t n, int K, int num_sms, int pin, int *ipt, int *grid_out, int *block_out) {
+  int I = 0, best = 1 << 30;
+  for (int c = std::max(pin, 1); c <= ts_persist_imax(K); ++c) {
+    if ((uint64_t)num_sms * ts_persist_tmax(K, c) * c < n) continue;
+    if (pin > 0) { I = c; break; }  // the knob pins the first I >= its value that fits
+    const uint64_t threads = (n + c - 1) / c;
+    const uint64_t grid = std::min<uint64_t>(num_sms, (threads + 63) / 64);
+    const int warps = (int)(((threads + grid - 1) / grid + 31) / 32);
+    const int score = std::max((warps + 3) / 4, 2);
+    if (score < best) { best = score; I = c; }
+  }
+  *ipt = I;
+  if (I == 0) {
+    *grid_out = num_sms;
+    *block_out = ts_persist_tmax(K, 0);
+    return;
+  }
+  const uint64_t threads = (n + I - 1) / I;
+  *grid_out = (int)std::max<uint64_t>(1, std::min<uint64_t>(num_sms, (threads + 63) / 64));  // all SMs once there are 2 warps each
+  const uint64_t t = (threads + *grid_out - 1) / *grid_out;
+  *block_out = (int)std::min<uint64_t>(ts_persist_tmax(K, I), std::max<uint64_t>(32, (t + 31) / 32 * 32));
+}
+
+int ts_plan_shard(uint64_t n_local, int k, int num_sms, int *ind_per_thread, int *grid, int *block) {
+  if (k < 1 || k > TS_MAX_K || num_sms < 1 || !ind_per_thread || !grid || !block)
+    return set_err(TS_ERR_ARG, "ts_plan_shard: K=%d outside 1..%d, num_sms=%d or null output", k, TS_MAX_K, num_sms);
+  plan_shard(n_local, k, num_sms, 0, ind_per_thread, grid, block);
+  return TS_OK;
+}
+
 int ts_create(const ts_config *cfg, ts_engine **out) {
   if (!cfg || !out) return set_err(TS_ERR_ARG, "ts_create: null argument");
   *out = nullptr;
@@ -635,40 +673,9 @@ int ts_create(const ts_config *cfg, ts_engine **out) {
     // same number of individuals (I = ceil(n / (SMs * TMAX))).
     const char *path = getenv("TSGPU_PATH");
     e->staged = path && !strcmp(path, "staged");
-    // I individuals per thread in registers: the smallest I whose thread cap covers the shard.
-    // Larger shards run the streaming variant of the same kernel (I = 0).
-    const uint64_t n = cfg->n_local;
-    int I = 0;
-    const char *force = getenv("TSGPU_IPT");  // developer knob: minimum individuals per thread
-    const int imin = force ? std::max(1, atoi(force)) : 1;
-    // Among the I that fit, take the one with the fewest warps on the busiest of the SM's four
-    // schedulers (the warp-level reduction and the CTA sum are issue-bound per scheduler), not going
-    // below two; ties go to the smaller I (shorter dependent FP64 chains, fewer registers).
-    // B200, K = 10, us per SVI iteration: 60K individuals I=1/13 warps 30.9, I=2/7 warps 28.3;
-    // 80K I=2/9 warps 30.9, I=3/6 warps 28.9; 100K I=2/11 warps 31.2, I=3/8 warps 29.7, I=4/6 warps 32.5.
-    int best = 1 << 30;
-    for (int c = imin; c <= ts_persist_imax(e->K); ++c) {
-      if ((uint64_t)e->num_sms * ts_persist_tmax(e->K, c) * c < n) continue;
-      if (force) { I = c; break; }  // the knob pins the first I >= its value that fits
-      const uint64_t threads = (n + c - 1) / c;
-      const uint64_t grid = std::min<uint64_t>(e->num_sms, (threads + 63) / 64);
-      const int warps = (int)(((threads + grid - 1) / grid + 31) / 32);
-      const int score = std::max((warps + 3) / 4, 2);
-      if (score < best) { best = score; I = c; }
-    }
-    if (I == 0) {
-      // beyond the register-resident capacity: the streaming variant (E read from L2 every round)
-      e->ind_per_thread = 0;
-      e->grid_persist = e->num_sms;
-      e->block_persist = ts_persist_tmax(e->K, 0);
-    } else {
-      const int tmax = ts_persist_tmax(e->K, I);
-      const uint64_t threads = (n + I - 1) / I;
-      e->ind_per_thread = I;
-      e->grid_persist = (int)std::min<uint64_t>(e->num_sms, (threads + 63) / 64);  // all SMs once there are 2 warps each
-      const uint64_t t = (threads + e->grid_persist - 1) / e->grid_persist;
-      e->block_persist = (int)std::min<uint64_t>(tmax, (t + 31) / 32 * 32);
-    }
+    const char *force = getenv("TSGPU_IPT");  // developer knob: pin the individuals per thread
+    plan_shard(cfg->n_local, e->K, e->num_sms, force ? std::max(1, atoi(force)) : 0, &e->ind_per_thread, &e->grid_persist,
+               &e->block_persist);
     int bits = 1;
     while ((2 * cfg->n_total + 2) >> bits) bits++;
     const int sh = 52 - bits;  // per-warp sums stay below 2^52 (mantissa-trick conversion)

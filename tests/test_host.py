@@ -225,3 +225,26 @@ def test_driver_host_logic_against_golden(fixture_case, tmp_path):
     assert val.shape == (10, 5) and val[:, 0].astype(int).tolist() == g["val_iter"].tolist()
     import hashlib
     assert hashlib.md5(open(tmp_path / "theta.txt", "rb").read()).hexdigest() == "ae1136d8769318e9840b1f7dd1d1ac53"
+
+
+def test_shard_plan_geometry():
+    """ts_plan_shard (host arithmetic behind ts_create): the persistent kernel's geometry covers the
+    shard, respects the per-(K, I) thread caps, and reproduces the choices the round-1 measurements
+    were made with (profiles/r1_summary.md)."""
+    import terastructure_b200 as ts
+    sms = 148
+    assert ts.plan_shard(100000, 10, sms) == (3, 148, 256)      # BASELINE configs[2] on one B200
+    assert ts.plan_shard(125000, 10, sms) == (4, 148, 224)      # configs[3] over 8 GPUs
+    assert ts.plan_shard(60000, 10, sms)[0] == 2 and ts.plan_shard(80000, 10, sms)[0] == 3
+    assert ts.plan_shard(400000, 10, sms)[0] == 0               # streaming variant
+    assert ts.plan_shard(200, 3, sms) == (1, 4, 64)             # the reference's bundled data set
+    for k in (1, 2, 6, 10, 12, 13, 16, 20, 21, 32):
+        for n in (1, 3, 31, 33, 200, 4097, 9999, 37888, 37889, 56000, 75776, 99999, 113664, 113665, 151552, 151553, 10 ** 6):
+            ipt, grid, block = ts.plan_shard(n, k, sms)
+            assert 1 <= grid <= sms and block % 32 == 0 and 32 <= block <= 512
+            if ipt:
+                assert 1 <= ipt <= 4 and grid * block * ipt >= n, (k, n, ipt, grid, block)
+            else:
+                assert grid == sms
+    with pytest.raises(ts.TsError):
+        ts.plan_shard(100, 33, sms)
