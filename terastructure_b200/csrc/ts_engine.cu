@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "ts_device.cuh"
+#include "ts_fixed.cuh"
 
 // ------------------------------------------------------------------------------------------
 // error plumbing
@@ -676,9 +677,7 @@ int ts_create(const ts_config *cfg, ts_engine **out) {
     const char *force = getenv("TSGPU_IPT");  // developer knob: pin the individuals per thread
     plan_shard(cfg->n_local, e->K, e->num_sms, force ? std::max(1, atoi(force)) : 0, &e->ind_per_thread, &e->grid_persist,
                &e->block_persist);
-    int bits = 1;
-    while ((2 * cfg->n_total + 2) >> bits) bits++;
-    const int sh = 52 - bits;  // per-warp sums stay below 2^52 (mantissa-trick conversion)
+    const int sh = tsfx::shift_for(cfg->n_total);  // per-warp sums stay below 2^52 (mantissa-trick conversion)
     e->prm.fx_scale = ldexp(1.0, sh);
     e->prm.fx_inv = ldexp(1.0, -sh);
     e->prm.trace = nullptr;

@@ -27,12 +27,12 @@
 //
 // No host round trip, no kernel launch and no fence on the critical path of a round.
 #pragma once
+#include "ts_fixed.cuh"
 
 namespace tsp {
 
-constexpr int FX_CNT_SHIFT = 54;
-constexpr unsigned long long FX_MASK = (1ull << FX_CNT_SHIFT) - 1;
-constexpr double FX_LO_SCALE = 17592186044416.0;  // 2^44
+constexpr int FX_CNT_SHIFT = tsfx::CNT_SHIFT;
+constexpr unsigned long long FX_MASK = tsfx::MASK;
 constexpr long long SPIN_LIMIT = 1ll << 23;
 
 // one level of the transposed reduction: lanes whose `bit` is clear keep the low half of the
@@ -208,8 +208,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
   const uint32_t GT = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
   const unsigned long long G = gridDim.x;
-  const double fx_hi_off = -4503599627370496.0 * p.fx_inv, fx_lo_inv = p.fx_inv * (1.0 / FX_LO_SCALE),
-               fx_lo_off = -4503599627370496.0 * fx_lo_inv;  // powers of two: exact
+  const tsfx::Unscale fxu = tsfx::unscale(p.fx_inv);
   const double big_thr = 2.0 * V * p.thresh;  // one |delta lambda| this large rules convergence out
 
   // which statistic this lane ends up holding after tr_reduce
@@ -446,11 +445,10 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
           // S_t[k] contribution of this warp = hi * 2^-sh + lo * 2^-(sh+44), hi = rint(sc) >= 0,
           // |lo| <= 2^43; both conversions are "add 2^52 and read the mantissa" (sc < 2^52)
           const double sc = (bx[v] * vv[q]) * p.fx_scale;
-          const double th = sc + 4503599627370496.0;
-          const double rem = sc - (th - 4503599627370496.0);
-          const double tl = fma(rem, FX_LO_SCALE, 6755399441055744.0);  // 2^52 + 2^51: signed
-          s_fix[v * WS + warp] = __double_as_longlong(th) - 0x4330000000000000ll;
-          s_fix[(V + v) * WS + warp] = __double_as_longlong(tl) - 0x4338000000000000ll;
+          long long whi, wlo;
+          tsfx::split(sc, whi, wlo);
+          s_fix[v * WS + warp] = whi;
+          s_fix[(V + v) * WS + warp] = wlo;
         }
       TS_TRACE(2 + 8 * x + 1);
       __syncthreads();
@@ -462,9 +460,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
 #pragma unroll
         for (int ww = 0; ww < WS - 1; ++ww)
           if (ww < W) { hi += sh[ww]; lo += sl[ww]; }
-        const long long carry = lo >> 44;  // floor: the low word becomes [0, 2^44)
-        hi += carry;
-        lo -= carry << 44;
+        tsfx::normalize(hi, lo);  // the low word becomes [0, 2^44)
         red_add(&st->acc[par][v][0], (unsigned long long)hi + (1ull << FX_CNT_SHIFT));
         red_add(&st->acc[par][V + v][0], (unsigned long long)lo + (1ull << FX_CNT_SHIFT));
       }
@@ -533,17 +529,12 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
                 for (int u = 0; u < 8; ++u)
                   if (r0 + u < p.nranks) { th += wh[u] & FX_MASK; tl += wl[u] & FX_MASK; }
               }
-              // every GPU's low word is below 148 * 2^44, but the sum over ranks can pass 2^52, the
-              // limit of the mantissa conversion below: move the carry into the high word (exact)
-              dh = th + (tl >> 44);
-              dl = tl & ((1ull << 44) - 1);
+              dh = th;
+              dl = tl;
+              tsfx::fold(dh, dl);  // the ranks' low words can add up to 2^52 and more: carry first
             }
           }
-          // u64 -> double through the mantissa (both < 2^52): (2^52 + d) * 2^-s - 2^(52-s) is exact,
-          // so each word costs one integer OR and one DFMA; the sum of the two rounds once
-          const double dhd = fma(__longlong_as_double((long long)(dh | 0x4330000000000000ull)), p.fx_inv, fx_hi_off);
-          const double dld = fma(__longlong_as_double((long long)(dl | 0x4330000000000000ull)), fx_lo_inv, fx_lo_off);
-          tot[q] = dhd + dld;
+          tot[q] = tsfx::to_double(dh, dl, fxu);  // u64 -> double through the mantissa (both < 2^52)
         }
         TS_TRACE(2 + 8 * x + 4);
         // new lambda -> new b first (the critical path of the round); convergence test afterwards

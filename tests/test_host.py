@@ -5,6 +5,7 @@ points fail loudly without a GPU."""
 import ctypes as C
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -248,3 +249,14 @@ def test_shard_plan_geometry():
                 assert grid == sms
     with pytest.raises(ts.TsError):
         ts.plan_shard(100, 33, sms)
+
+
+def test_fixed_point_words_host_check(tmp_path):
+    """ts_fixed.cuh compiled for the host (the same source the persistent kernel inlines): split /
+    normalize / arrival counts / fold over ranks / to_double are exact, order-independent, survive the
+    wrap-around of the monotonic words, and the >= 2^52 low-word sum over 4+ GPUs is carried."""
+    exe = str(tmp_path / "fx_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "terastructure_b200", "csrc"),
+                    "-o", exe, os.path.join(ROOT, "tests", "fx_check.cpp")], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
