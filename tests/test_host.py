@@ -260,3 +260,30 @@ def test_fixed_point_words_host_check(tmp_path):
                     "-o", exe, os.path.join(ROOT, "tests", "fx_check.cpp")], check=True)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
+
+
+def test_exp_digamma_host_model_vs_mpmath(tmp_path):
+    """ts_expsi.cuh compiled for the host (the kernel's own source; the MUFU reciprocal seed modelled
+    by a 20-bit reciprocal): f = exp(digamma), fast_rcp and exp_neg against mpmath."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    exe = str(tmp_path / "expsi_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "terastructure_b200", "csrc"),
+                    "-o", exe, os.path.join(ROOT, "tests", "expsi_check.cpp")], check=True)
+    out = subprocess.run([exe, "1200"], capture_output=True, text=True, check=True).stdout
+    worst = {"large": 0.0, "mid": 0.0, "small": 0.0, "rcp": 0.0, "exp": 0.0}
+    for line in out.splitlines():
+        x, f, r, e = (float.fromhex(t) for t in line.split())
+        X = mp.mpf(x)
+        ref = mp.exp(mp.digamma(X))
+        err = abs(float((mp.mpf(f) - ref) / ref)) if ref > mp.mpf("1e-290") else abs(f)
+        key = "large" if x >= 8 else ("mid" if x >= 0.03 else "small")
+        worst[key] = max(worst[key], err)
+        worst["rcp"] = max(worst["rcp"], abs(float(mp.mpf(r) * X - 1)))
+        y = x if x < 750.0 else 750.0 + 1e-7 * x
+        if y <= 700.0:
+            worst["exp"] = max(worst["exp"], abs(float(mp.mpf(e) / mp.exp(-mp.mpf(y)) - 1)))
+        else:
+            assert e == 0.0
+    assert worst["large"] < 5e-16 and worst["mid"] < 1e-14 and worst["small"] < 3e-13, worst
+    assert worst["rcp"] < 2.3e-16 and worst["exp"] < 1e-14, worst
