@@ -342,9 +342,10 @@ def test_staged_path_matches_persistent(monkeypatch):
 
 
 def test_exp_digamma_table_on_device():
-    """The persistent kernel's table-driven exp(digamma(x)) against mpmath-grade SciPy values:
-    E is not exposed, so check its effect -- one SVI step on a single-locus problem where
-    gamma spans the whole table range must match the oracle (which uses log/exp/series)."""
+    """The persistent kernel's exp(digamma(x)) (ts_expsi.cuh: series for x >= 8, recurrence + exp
+    below) on the device: E is not exposed, so check its effect -- SVI steps on a problem whose
+    gamma spans 0.04 .. 3e6 must match the oracle (which uses log/exp/series).  The host model of
+    the same source is checked against mpmath in test_host.py."""
     import terastructure_b200 as ts
     from terastructure_b200 import plink
     n, l, k = 2048, 201, 4
