@@ -65,6 +65,17 @@ def profiled_traffic_bytes(iters_per_launch):
         return None
 
 
+def kernel_label(ts, n_per, k):
+    """Name and launch geometry of the dominant kernel for a shard of n_per individuals."""
+    label = "tsp::k_persist<%d" % k
+    try:
+        ipt, grid, block = ts.plan_shard(n_per, k)
+        label += ",%d>, %d CTAs x %d threads" % (ipt, grid, block)
+    except Exception:
+        label += ">"
+    return label + " (one cooperative launch per step = BATCH SVI iterations)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -339,7 +350,7 @@ def main():
                          "traffic": profiled_traffic_bytes(BATCH) if (world == 1 and K == 10 and n_per == N_ONE_GPU) else None,
                          "traffic_note": "dram__bytes_read+write per launch from profiles/ (ncu --set full), bytes",
                          "peak_source": peak_src,
-                         "kernel": "tsp::k_persist<10> (one cooperative launch per step = BATCH SVI iterations)",
+                         "kernel": kernel_label(ts, n_per, K),
                          "algorithmic_bytes_per_genotype": bpg},
             "wall_s_timed_region": t_wall, "mean_rounds_per_snp": rounds_total / (BATCH * args.steps),
             "us_per_svi_iteration": 1e3 * dev_ms / (BATCH * args.steps),
