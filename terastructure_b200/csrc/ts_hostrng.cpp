@@ -131,17 +131,24 @@ int ts_sample_validation(ts_rng *r, uint64_t n, uint64_t l, const uint8_t *bed, 
   if (!r || n == 0 || l == 0 || n > 0xffffffffull || l > 0xffffffffull) return TS_ERR_ARG;
   const uint32_t per_loc_h = (uint32_t)(n < 2000 ? n / 10 : n / 100);
   const uint64_t nlocs = (uint64_t)(l * 0.005);
+  // One N-bit bitmap, reused locus by locus (the reference draws a locus, then all of its held-out
+  // individuals, before the next locus); every locus holds exactly per_loc_h individuals, so the
+  // ascending lists go straight into the output array in DRAW order and the blocks are then
+  // permuted in place into ascending-locus order.  Peak memory = the output itself
+  // (200 MB at 1M x 1M) + N/8 bytes.
+  const size_t h = per_loc_h;
+  const size_t cap = (size_t)(nlocs ? nlocs : 1);
   std::vector<uint8_t> taken(l, 0);
   std::vector<uint32_t> drawn;
-  std::vector<std::vector<uint64_t>> masks;
+  drawn.reserve(cap);
   const size_t words = (n + 63) / 64;
+  std::vector<uint64_t> m(words, 0ull);
+  uint32_t *vi = (uint32_t *)malloc(sizeof(uint32_t) * (cap * h + 1));
+  if (!vi) return TS_ERR_ARG;
   do {
     const uint32_t loc = r->uniform_int((uint32_t)l);
     if (taken[loc]) continue;
     taken[loc] = 1;
-    drawn.push_back(loc);
-    masks.emplace_back(words, 0ull);
-    std::vector<uint64_t> &m = masks.back();
     const uint8_t *row = bed ? bed + (size_t)loc * row_pitch : nullptr;
     uint32_t c = 0;
     while (c < per_loc_h) {
@@ -153,6 +160,17 @@ int ts_sample_validation(ts_rng *r, uint64_t n, uint64_t l, const uint8_t *bed, 
         c++;
       }
     }
+    uint32_t *blk = vi + drawn.size() * h;
+    size_t q = 0;
+    for (size_t w = 0; w < words && q < h; ++w) {
+      uint64_t bits = m[w];
+      m[w] = 0;
+      while (bits) {
+        blk[q++] = (uint32_t)(w * 64 + __builtin_ctzll(bits));
+        bits &= bits - 1;
+      }
+    }
+    drawn.push_back(loc);
   } while (drawn.size() < nlocs);
 
   const size_t nv = drawn.size();
@@ -161,22 +179,30 @@ int ts_sample_validation(ts_rng *r, uint64_t n, uint64_t l, const uint8_t *bed, 
   std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return drawn[a] < drawn[b]; });
   uint32_t *vl = (uint32_t *)malloc(sizeof(uint32_t) * (nv ? nv : 1));
   uint64_t *vo = (uint64_t *)malloc(sizeof(uint64_t) * (nv + 1));
-  uint32_t *vi = (uint32_t *)malloc(sizeof(uint32_t) * (nv * (size_t)per_loc_h + 1));
-  if (!vl || !vo || !vi) { free(vl); free(vo); free(vi); return TS_ERR_ARG; }
-  size_t p = 0;
+  if (!vl || !vo) { free(vl); free(vo); free(vi); return TS_ERR_ARG; }
   for (size_t i = 0; i < nv; ++i) {
     vl[i] = drawn[order[i]];
-    vo[i] = p;
-    const std::vector<uint64_t> &m = masks[order[i]];
-    for (size_t w = 0; w < words; ++w) {
-      uint64_t bits = m[w];
-      while (bits) {
-        const int b = __builtin_ctzll(bits);
-        vi[p++] = (uint32_t)(w * 64 + b);
-        bits &= bits - 1;
+    vo[i] = i * h;
+  }
+  // gather the blocks in place: block i of the result is block order[i] of the draw order
+  {
+    std::vector<uint32_t> tmp(h ? h : 1);
+    std::vector<uint8_t> done(nv, 0);
+    for (size_t s0 = 0; s0 < nv && h; ++s0) {
+      if (done[s0]) continue;
+      if (order[s0] == s0) { done[s0] = 1; continue; }
+      memcpy(tmp.data(), vi + s0 * h, h * sizeof(uint32_t));
+      size_t j = s0;
+      for (;;) {
+        const size_t src = order[j];
+        done[j] = 1;
+        if (src == s0) { memcpy(vi + j * h, tmp.data(), h * sizeof(uint32_t)); break; }
+        memcpy(vi + j * h, vi + src * h, h * sizeof(uint32_t));
+        j = src;
       }
     }
   }
+  const size_t p = nv * h;
   vo[nv] = p;
   *nval_out = nv;
   *val_loc_out = vl;

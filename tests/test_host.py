@@ -287,3 +287,19 @@ def test_exp_digamma_host_model_vs_mpmath(tmp_path):
             assert e == 0.0
     assert worst["large"] < 5e-16 and worst["mid"] < 1e-14 and worst["small"] < 3e-13, worst
     assert worst["rcp"] < 2.3e-16 and worst["exp"] < 1e-14, worst
+
+
+@pytest.mark.parametrize("n,l,seed", [(2500, 1800, 99), (150, 1200, 3)])
+def test_validation_sampler_with_missing_genotypes(n, l, seed):
+    """set_validation_sample (cc:196-224) with 3 % missing genotypes (kv_ok rejects them, which shifts
+    the RNG stream): the host sampler (one reusable bitmap, blocks permuted in place) against the
+    oracle's restatement, for both N >= 2000 (N/100 per locus) and N < 2000 (N/10)."""
+    import terastructure_b200 as ts
+    from terastructure_b200 import plink
+    rs = np.random.RandomState(seed)
+    y = rs.randint(0, 3, size=(l, n)).astype(np.uint8)
+    y[rs.rand(l, n) < 0.03] = 3
+    o = ol.Oracle(y, 3, seed)
+    ovl, ovo, ovi = o.validation()
+    vl, vo, vi = ts.Rng(seed).sample_validation(n, l, plink.pack(y))
+    assert np.array_equal(vl, ovl) and np.array_equal(vo, ovo) and np.array_equal(vi, ovi)
