@@ -303,3 +303,29 @@ def test_validation_sampler_with_missing_genotypes(n, l, seed):
     ovl, ovo, ovi = o.validation()
     vl, vo, vi = ts.Rng(seed).sample_validation(n, l, plink.pack(y))
     assert np.array_equal(vl, ovl) and np.array_equal(vo, ovo) and np.array_equal(vi, ovi)
+
+
+def test_validation_sampler_matches_stream_emulation():
+    """300 validation loci (long cycles in the in-place block permutation): every locus keeps its own
+    held-out individuals, and the RNG stream ends where a draw-by-draw emulation of
+    set_validation_sample (cc:196-224) ends."""
+    import terastructure_b200 as ts
+    n, l, seed = 3000, 60000, 5
+    r = ts.Rng(seed)
+    vl, vo, vi = r.sample_validation(n, l, None)
+    q = ts.Rng(seed)
+    h, nlocs = n // 100, int(l * 0.005)
+    taken, out = set(), {}
+    while len(out) < nlocs:
+        loc = int(q.sample_locs(l, 1)[0])
+        if loc in taken:
+            continue
+        taken.add(loc)
+        s = set()
+        while len(s) < h:
+            s.add(int(q.sample_locs(n, 1)[0]))
+        out[loc] = sorted(s)
+    assert list(vl) == sorted(out)
+    for i, loc in enumerate(sorted(out)):
+        assert list(vi[vo[i]:vo[i + 1]]) == out[loc]
+    assert int(r.sample_locs(1000, 1)[0]) == int(q.sample_locs(1000, 1)[0])
