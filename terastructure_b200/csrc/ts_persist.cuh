@@ -17,13 +17,14 @@
 //             counts arrivals in its top 10 bits, so the grid barrier needs no fence and no
 //             separate flag: one L2 round trip to publish, one to observe.  The words are
 //             monotonic (never reset); two sets alternate by round parity and every CTA remembers
-//             the previous total of each set.  One lane per CTA spins (on the last word); the
-//             others read their words once that one is complete.  Words sit 1 KB apart so that
-//             they spread over the L2 slices.
+//             the previous total of each set.  Lane v of the control warp spins on the two words
+//             of statistic v.  Words sit 1 KB apart so that they spread over the L2 slices.
 //       multi-GPU: CTA 0 stores the GPU's integer totals (tagged with the round number) into its
 //             slot on every peer over NVLink; every CTA of every GPU adds the slots in rank order.
 //       warp 0 of every CTA (redundantly, bit-identically): lambda, convergence test, new b
-//     gamma step + E = f(gamma) refresh for the CTA's individuals (skipped in hol mode)
+//     gamma step + E = f(gamma) refresh for the CTA's individuals (skipped in hol mode); when all
+//     permitted rounds run it starts right after the last round's arrivals, in the shadow of that
+//     round's barrier, and the last warp first prepares b for the next SNP's first round
 //
 // No host round trip, no kernel launch and no fence on the critical path of a round.
 #pragma once
