@@ -108,4 +108,26 @@ TSFX_HD int shift_for(unsigned long long n_total) {
   return 52 - bits;
 }
 
+// Which of the V per-thread partial sums a lane holds after the transposed warp reduction
+// (tr_reduce in ts_persist.cuh): level by level (lane bits 16, 8, 4, 2, 1) a lane keeps the lower
+// ceil(n/2) of the n live values if its bit is clear, the upper floor(n/2) otherwise.  The split uses
+// the NOMINAL count ceil(n/2), the same for every lane; a lane that took a short upper half carries
+// zero padding, so its live count `len` can be smaller than the nominal one (0 for V < 32 on some lanes).
+template <int V>
+TSFX_HD void tr_slot(int lane, int &start, int &len) {
+  start = 0;
+  len = V;
+  int nominal = V;
+#pragma unroll
+  for (int bit = 16; bit > 0; bit >>= 1) {
+    const int lo = (nominal + 1) / 2;
+#if defined(__CUDA_ARCH__)
+    if (lane & bit) { start += lo; len = max(len - lo, 0); } else len = min(len, lo);
+#else
+    if (lane & bit) { start += lo; len = len - lo > 0 ? len - lo : 0; } else len = len < lo ? len : lo;
+#endif
+    nominal = lo;
+  }
+}
+
 }  // namespace tsfx

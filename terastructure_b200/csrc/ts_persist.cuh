@@ -133,19 +133,9 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
   const tsfx::Unscale fxu = tsfx::unscale(p.fx_inv);
   const double big_thr = 2.0 * V * p.thresh;  // one |delta lambda| this large rules convergence out
 
-  // which statistic this lane ends up holding after tr_reduce
-  // (tr_level splits a NOMINAL count that is the same for every lane; a lane that took a short
-  // upper half carries zero padding, so its live count can be smaller than the nominal one)
-  int tr_start = 0, tr_len = V;
-  {
-    int nominal = V;
-#pragma unroll
-    for (int bit = 16; bit > 0; bit >>= 1) {
-      const int lo = (nominal + 1) / 2;
-      if (lane & bit) { tr_start += lo; tr_len = max(tr_len - lo, 0); } else tr_len = min(tr_len, lo);
-      nominal = lo;
-    }
-  }
+  // which statistics this lane ends up holding after tr_reduce
+  int tr_start, tr_len;
+  tsfx::tr_slot<V>(lane, tr_start, tr_len);
 
   // control-warp state: previous totals of the two word sets, current lambda row
   unsigned long long ph0[VPL], pl0[VPL], ph1[VPL], pl1[VPL];

@@ -329,3 +329,14 @@ def test_validation_sampler_matches_stream_emulation():
     for i, loc in enumerate(sorted(out)):
         assert list(vi[vo[i]:vo[i + 1]]) == out[loc]
     assert int(r.sample_locs(1000, 1)[0]) == int(q.sample_locs(1000, 1)[0])
+
+
+def test_transposed_reduction_slot_mapping(tmp_path):
+    """tsfx::tr_slot (which statistics a lane holds after the kernel's transposed warp reduction)
+    against a lock-step host emulation of the shuffle network, for every V = 2K, K = 1..32 (the
+    mapping uses nominal, not live, counts: V = 10, 20, 26, 40 were wrong once)."""
+    exe = str(tmp_path / "tr_check")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "terastructure_b200", "csrc"),
+                    "-o", exe, os.path.join(ROOT, "tests", "tr_check.cpp")], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout[-2000:]
