@@ -150,6 +150,13 @@ int ts_get_lambda(ts_engine *e, uint64_t loc_begin, uint64_t nloc, double *out /
 int ts_get_beta(ts_engine *e, uint64_t loc_begin, uint64_t nloc, double *out /* nloc x K */);
 int ts_sync(ts_engine *e);
 
+/* Waits inside the kernels (grid barrier, peer exchange) are bounded by a wall-clock limit
+ * (TSGPU_TIMEOUT_S in the environment at ts_create, default 60 s).  All ranks of an exchange group
+ * must therefore enter ts_steps / ts_heldout_ll with the same work within that time of each other
+ * (a host barrier before the first exchange is enough).  After a timeout the call returns
+ * TS_ERR_CUDA ("barrier timed out") from the next synchronising call and the engine's state is
+ * undefined: destroy it. */
+
 /* ---- multi-GPU exchange (replaces the main thread's sum over workers' lambdat,
  *      snpsamplinge.cc:337-352) ------------------------------------------------------------
  * Individuals are sharded; each round every engine publishes its 2K partial sums into a
@@ -168,6 +175,10 @@ int ts_comm_connect_local(ts_engine **engines, int n);
  * CTAs and threads per CTA.  The reference's counterpart is the static split of individuals over
  * `-nthreads` workers (split_all_indivs, snpsamplinge.cc:298-318). */
 int ts_plan_shard(uint64_t n_local, int k, int num_sms, int *ind_per_thread, int *grid, int *block);
+/* The geometry this engine runs with.  It differs from ts_plan_shard's only under the test knob
+ * TSGPU_IPT=<i> (environment, read by ts_create), which pins the individuals per thread (0 = the
+ * streaming variant) so that parity tests reach every kernel instantiation at oracle-sized inputs. */
+int ts_get_plan(const ts_engine *e, int *ind_per_thread, int *grid, int *block);
 
 /* ---- profiling hooks ------------------------------------------------------------------- */
 /* Kernels launched by this engine since creation (for bench.py's gpu_launches). */

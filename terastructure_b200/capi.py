@@ -60,6 +60,7 @@ EXPORTS = {
     "ts_comm_connect": (_i, [_vp, _vp]),
     "ts_comm_connect_local": (_i, [C.POINTER(_vp), _i]),
     "ts_plan_shard": (_i, [_u64, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "ts_get_plan": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "ts_launch_count": (_u64, [_vp]),
     "ts_timer_start": (_i, [_vp]),
     "ts_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
@@ -281,6 +282,13 @@ class Engine:
         blob = b"".join(handles)
         assert len(blob) == TS_COMM_HANDLE_BYTES * self.cfg.nranks
         check(lib().ts_comm_connect(self._h, blob))
+
+    @property
+    def plan(self):
+        """(individuals per thread, CTAs, threads per CTA) of this engine's persistent kernel."""
+        ipt, grid, block = C.c_int(), C.c_int(), C.c_int()
+        check(lib().ts_get_plan(self._h, C.byref(ipt), C.byref(grid), C.byref(block)))
+        return ipt.value, grid.value, block.value
 
     @property
     def launch_count(self):

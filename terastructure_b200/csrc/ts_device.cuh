@@ -89,7 +89,8 @@ struct Params {
   PState *pst;
   PState *pst_peer[MAXR];
   double fx_scale, fx_inv;  // 2^sh and 2^-sh of the fixed-point statistics
-  int xflush;               // fence.sys after the peer stores (TSGPU_XFLUSH, default on)
+  int xflush;               // fence.sys after the peer stores (TSGPU_XFLUSH, default off)
+  unsigned long long timeout_ns;  // wall-clock limit of one grid/peer wait (TSGPU_TIMEOUT_S, default 60 s)
   long long *trace;         // optional phase trace of CTA 0 (TSGPU_TRACE=1), 64 items x 128 slots
 };
 

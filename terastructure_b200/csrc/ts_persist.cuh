@@ -35,7 +35,6 @@ namespace tsp {
 
 constexpr int FX_CNT_SHIFT = tsfx::CNT_SHIFT;
 constexpr unsigned long long FX_MASK = tsfx::MASK;
-constexpr long long SPIN_LIMIT = 1ll << 23;
 
 // one level of the transposed reduction: lanes whose `bit` is clear keep the low half of the
 // N live values, the others the high half; each lane adds what its partner held of its half.
@@ -90,11 +89,40 @@ __device__ __forceinline__ void red_add(unsigned long long *p, unsigned long lon
 __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+// A lambda row travels between CTAs inside a launch (CTA 0 publishes the converged row; every CTA
+// reads rows of loci it revisits): strong (L2-coherent) accesses, ordered by fence_gpu() on both
+// sides of the grid barrier that separates the store from the loads (see "row hand-off" below).
+__device__ __forceinline__ double ld_row(const double *p) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_row(double *p, double v) {
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Poll loops give up after Params::timeout_ns of WALL CLOCK (a lost CTA or rank), checked every 4096
+// polls so that the timer read stays off the fast path.
+struct SpinGuard {
+  unsigned long long t0 = 0;
+  unsigned spins = 0;
+  __device__ __forceinline__ bool expired(unsigned long long limit_ns) {
+    if ((++spins & 4095u) != 0) return false;
+    const unsigned long long now = global_ns();
+    if (t0 == 0) { t0 = now; return false; }
+    return now - t0 > limit_ns;
+  }
+};
 
 // Optional phase trace (TSGPU_TRACE=1): CTA 0 / thread 0 stamps clock64() at phase boundaries.
 #define TS_TRACE(slot)                                                                        \
   do {                                                                                        \
-    if (p.trace && blockIdx.x == 0 && tid == 0 && i < 64)                                     \
+    if (p.trace && blockIdx.x == 0 && tid == 0 && i < 64 && (unsigned)(slot) < 128u)          \
       p.trace[(size_t)i * 128 + (slot)] = clock64();                                          \
   } while (0)
 
@@ -111,7 +139,7 @@ __host__ __device__ constexpr int persist_tmax(int K, int I) {
                  : (K <= 20 ? (I == 1 ? 384 : (I == 2 ? 256 : (I == 3 ? 224 : 192))) : 256);
 }
 __host__ __device__ constexpr size_t persist_smem_bytes(int K, int I) {
-  return sizeof(double) * (8 * K) + sizeof(long long) * (4 * K * (persist_tmax(K, I) / 32 + 1)) + 16;
+  return sizeof(double) * (12 * K) + sizeof(long long) * (4 * K * (persist_tmax(K, I) / 32 + 1)) + 16;
 }
 
 template <int K, int I>
@@ -123,7 +151,8 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *s_b = reinterpret_cast<double *>(smem_raw);                // [2][V]: b of round x >= 1 at [x&1]
   double *s_b0 = s_b + 2 * V;                                        // [2][V]: b of round 0 of SNP i at [i&1]
-  long long *s_fix = reinterpret_cast<long long *>(s_b0 + 2 * V);    // [NW][WS] per-warp fixed-point words
+  double *s_row0 = s_b0 + 2 * V;                                     // [2][V]: the lambda row that b came from
+  long long *s_fix = reinterpret_cast<long long *>(s_row0 + 2 * V);  // [NW][WS] per-warp fixed-point words
   int *s_flag = reinterpret_cast<int *>(s_fix + NW * WS);  // bit 0: round loop done, bit 1: abort
 
   PState *st = p.pst;
@@ -193,12 +222,19 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
     // b of round 0 comes from the stored lambda row (estimate_beta, cc:279-296).  A helper warp
     // prepared it while the previous SNP's gamma step ran, unless this is the launch's first SNP or
     // the same locus again (its row was not final then): the control warp does it here in that case.
-    auto b_from_row = [&](uint32_t loc, double *dst) {
+    //
+    // Row hand-off inside a launch: CTA 0 publishes a locus' converged row (st_row) and fences before
+    // its next arrival on the grid barrier (see the publish step); a CTA reads the row of a locus
+    // only after it has passed that barrier, with strong loads behind a fence.  With a single
+    // permitted round the helper would run BEFORE this SNP's only barrier, i.e. possibly before CTA 0
+    // has stored the row of the SNP before it (locus sequence A, B, A): no preparation then.
+    auto b_from_row = [&](uint32_t loc, double *dst, double *row_dst) {
       double own[VPL];
+      fence_gpu();
 #pragma unroll
       for (int q = 0; q < VPL; ++q) {
         const int v = lane + 32 * q;
-        own[q] = (v < V) ? __ldcg(p.lambda + (size_t)loc * V + v) : 1024.0;
+        own[q] = (v < V) ? ld_row(p.lambda + (size_t)loc * V + v) : 1024.0;
       }
 #pragma unroll
       for (int q = 0; q < VPL; ++q) {
@@ -209,17 +245,25 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
         s += l0;
         s += l1;
         const double b = f_expsi(own[q]) * fast_rcp(f_expsi(s));
-        if (v < V) dst[v] = b;
+        if (v < V) { dst[v] = b; row_dst[v] = own[q]; }
       }
     };
-    const bool prepared = i > 0 && it.loc != prev_loc;
+    const bool can_prepare = p.max_rounds >= 2;
+    const bool prepared = can_prepare && i > 0 && it.loc != prev_loc;
     double *b_first = s_b0 + (i & 1) * V;
     if (warp == 0) {
-      if (it.loc != prev_loc) {
+      if (prepared) {  // the helper left the row next to b
 #pragma unroll
         for (int q = 0; q < VPL; ++q) {
           const int v = lane + 32 * q;
-          lam[q] = (v < V) ? __ldcg(p.lambda + (size_t)it.loc * V + v) : 1024.0;
+          lam[q] = (v < V) ? s_row0[(i & 1) * V + v] : 1024.0;
+        }
+      } else if (it.loc != prev_loc) {
+        fence_gpu();
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+          const int v = lane + 32 * q;
+          lam[q] = (v < V) ? ld_row(p.lambda + (size_t)it.loc * V + v) : 1024.0;
         }
       }
       if (!prepared) {
@@ -239,9 +283,9 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
     }
     // the helper's job for the NEXT SNP; called once per SNP by warp W-1, before its gamma step
     auto prepare_next = [&]() {
-      if (warp == W - 1 && i + 1 < n_items) {
+      if (can_prepare && warp == W - 1 && i + 1 < n_items) {
         const uint32_t nloc = p.items[i + 1].loc;
-        if (nloc != it.loc) b_from_row(nloc, s_b0 + ((i + 1) & 1) * V);
+        if (nloc != it.loc) b_from_row(nloc, s_b0 + ((i + 1) & 1) * V, s_row0 + ((i + 1) & 1) * V);
         __syncwarp();
       }
     };
@@ -373,6 +417,9 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
         for (int ww = 0; ww < WS - 1; ++ww)
           if (ww < W) { hi += sh[ww]; lo += sl[ww]; }
         tsfx::normalize(hi, lo);  // the low word becomes [0, 2^44)
+        // row hand-off: these lanes of CTA 0 stored the previous SNP's row; by now that store has
+        // long been performed, so the fence that orders it before this arrival waits for nothing
+        if (x == 0 && blockIdx.x == 0) fence_gpu();
         red_add(&st->acc[par][v][0], (unsigned long long)hi + (1ull << FX_CNT_SHIFT));
         red_add(&st->acc[par][V + v][0], (unsigned long long)lo + (1ull << FX_CNT_SHIFT));
       }
@@ -395,7 +442,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
           const int v = lane + 32 * q;
           unsigned long long dh = 0, dl = 0;
           if (v < V) {
-            long long spins = 0;
+            SpinGuard guard;
             // single GPU: every CTA waits for the local words.  Several GPUs: only CTA 0 does (it
             // forwards the GPU's totals); the other CTAs wait for the rank slots alone, which keeps
             // the pollers off the words the arrivals are being added to.
@@ -405,7 +452,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
                 dh = ld_relaxed(&st->acc[par][v][0]) - bh;
                 dl = ld_relaxed(&st->acc[par][V + v][0]) - bl;
                 if ((dh >> FX_CNT_SHIFT) == G && (dl >> FX_CNT_SHIFT) == G) break;
-                if (++spins > SPIN_LIMIT) { abort = true; break; }
+                if (guard.expired(p.timeout_ns)) { abort = true; break; }
               }
               if (par) { ph1[q] = bh + dh; pl1[q] = bl + dl; } else { ph0[q] = bh + dh; pl0[q] = bl + dl; }
               dh &= FX_MASK;
@@ -427,7 +474,6 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
                   if (r0 + u < p.nranks) pending |= 1u << u;
-                spins = 0;
                 while (pending) {
 #pragma unroll
                   for (int u = 0; u < 8; ++u)
@@ -435,7 +481,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
 #pragma unroll
                   for (int u = 0; u < 8; ++u)
                     if ((pending & (1u << u)) && (wh[u] & ~FX_MASK) == tag && (wl[u] & ~FX_MASK) == tag) pending &= ~(1u << u);
-                  if (++spins > SPIN_LIMIT) { abort = true; break; }
+                  if (guard.expired(p.timeout_ns)) { abort = true; break; }
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
@@ -493,7 +539,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
         if (done && blockIdx.x == 0) {
 #pragma unroll
           for (int q = 0; q < VPL; ++q)
-            if (lane + 32 * q < V) p.lambda[(size_t)it.loc * V + lane + 32 * q] = own[q];
+            if (lane + 32 * q < V) st_row(p.lambda + (size_t)it.loc * V + lane + 32 * q, own[q]);
         }
         if (lane == 0) {
           if (abort) { st->fault = 1; *s_flag = 2; }

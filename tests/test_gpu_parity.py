@@ -508,3 +508,143 @@ def test_invariants_at_full_bench_size():
         assert abs(lam[:, 1].sum() - k - (2 - y[ok]).sum()) < 1e-7 * n
     s, c, per = e.heldout_ll(first=True)      # 5 * 10^6 held-out genotypes at Ebeta = 1/2
     assert c == 5_000_000 and np.isfinite(s) and -2.0 < s / c < -0.5
+
+
+# ------------------------------------------------------------------------------------------------
+# Every instantiation of the persistent kernel against the oracle (the kernels that
+# BENCH/SCALE time -- <10,3> and <10,4> -- and the streaming variant had only been checked through
+# sum-over-k invariants).  TSGPU_IPT pins the individuals per thread at oracle-sized inputs.
+# ------------------------------------------------------------------------------------------------
+def _oracle_vs_engine(y, k, seed, nsteps, extra_locs=(), tol=TIGHT, online_iterations=10):
+    """SNPSamplingE-style init (validation set, gamma) + a batch of SVI iterations that includes
+    training visits to validation loci, an immediate repeat and an A,B,A pattern; returns the engine."""
+    import terastructure_b200 as ts
+    from terastructure_b200 import plink
+    l, n = y.shape
+    rows = plink.pack(y)
+    r = ts.Rng(seed)
+    vl, vo, vi = r.sample_validation(n, l, rows)
+    g0 = r.init_gamma(n, k)
+    e = ts.Engine(n, l, k, online_iterations=online_iterations)
+    e.load_bed(rows)
+    e.set_validation(vl, vo, vi)
+    e.set_gamma(g0)
+    o = ol.Oracle(y, k, seed, online_iterations=online_iterations)
+    np.testing.assert_array_equal(vl, o.validation()[0])
+    np.testing.assert_array_equal(g0, o.gamma)
+    locs = [o.sample_loc() for _ in range(nsteps)]
+    if len(vl):
+        locs[1] = int(vl[0])                      # training visit to a validation locus (kv_ok)
+    locs[3] = locs[2]                             # same locus twice in a row
+    locs[6] = locs[4]                             # A, B, A
+    locs += [int(x) for x in extra_locs]
+    rounds = e.steps(np.array(locs, np.uint32), want_rounds=True)
+    ro = [o.train_loc(x) for x in locs]
+    o.flush()
+    assert rounds.tolist() == ro
+    assert rel_err(e.gamma, o.gamma) < tol
+    assert rel_err(e.get_lambda(), o.lam) < tol
+    assert rel_err(e.theta, o.theta) < tol
+    np.testing.assert_array_equal(e.counts, o.counts)
+    # held-out pass through the same kernel in hol mode
+    _, cnt, per = e.heldout_ll(False)
+    _, a, cnt_o, per_o = o.heldout(first=False, per_locus=True)
+    assert cnt == cnt_o
+    np.testing.assert_allclose(per, per_o, rtol=1e-10, atol=1e-12)
+    assert rel_err(e.get_lambda(), o.lam) < tol
+    return e
+
+
+@pytest.mark.parametrize("k", [10, 20])
+@pytest.mark.parametrize("ipt", [0, 1, 2, 3, 4])
+def test_forced_instantiation_vs_oracle(ipt, k, monkeypatch):
+    """k_persist<K, I> for I = 1..4 and the streaming variant (I = 0), ragged N, missing data."""
+    from terastructure_b200 import synth
+    monkeypatch.setenv("TSGPU_IPT", str(ipt))
+    n, l = 1501, 400
+    y, _, _ = synth.psd_genotypes(n, l, k, seed=5, missing_rate=0.03)
+    e = _oracle_vs_engine(y, k, 31 + ipt, 40)
+    assert e.plan[0] == ipt
+
+
+def test_config1_shape_vs_oracle():
+    """BASELINE configs[1] shape: 10 000 individuals, K = 6 (L cut to 400), 200 SVI iterations."""
+    from terastructure_b200 import synth
+    y, _, _ = synth.psd_genotypes(10_000, 400, 6, seed=3, missing_rate=0.01)
+    e = _oracle_vs_engine(y, 6, 1234, 200)
+    assert e.plan[1] == 148
+
+
+@pytest.mark.parametrize("n,ipt,block", [(100_000, 3, 256), (125_000, 4, 224)])
+def test_bench_geometry_vs_oracle(n, ipt, block):
+    """The exact kernels BENCH and SCALE time -- k_persist<10,3> at 148 x 256 (100 000 individuals,
+    BASELINE configs[2]) and k_persist<10,4> at 148 x 224 (125 000 per GPU, configs[3] / 8) --
+    against the sequential oracle: 20 SVI iterations incl. a validation locus, then a held-out pass."""
+    from terastructure_b200 import synth
+    y, _, _ = synth.psd_genotypes(n, 400, 10, seed=3, missing_rate=0.005)
+    e = _oracle_vs_engine(y, 10, 1234, 20)
+    assert e.plan == (ipt, 148, block)
+
+
+def test_streaming_variant_large_shard_vs_oracle():
+    """The streaming variant at a size that selects it by itself (beyond 148 x 256 x 4 individuals)."""
+    from terastructure_b200 import synth
+    y, _, _ = synth.psd_genotypes(160_000, 200, 4, seed=9, missing_rate=0.01)
+    e = _oracle_vs_engine(y, 4, 7, 12)
+    assert e.plan[0] == 0
+
+
+@pytest.mark.parametrize("ipt", [1, 3])
+def test_single_round_revisit_pattern(ipt, monkeypatch):
+    """online_iterations = 1: no grid barrier separates CTA 0's store of a locus' row from another
+    CTA's read of it when the locus sequence is A, B, A: rows must not be read early."""
+    from terastructure_b200 import synth
+    monkeypatch.setenv("TSGPU_IPT", str(ipt))
+    y, _, _ = synth.psd_genotypes(30_011, 64, 5, seed=8, missing_rate=0.02)
+    _oracle_vs_engine(y, 5, 3, 10, extra_locs=[3, 9, 3, 9, 3, 9, 9, 3] * 6, online_iterations=1)
+
+
+def test_two_devices_match_one():
+    """Real NVLink exchange: one engine per device (ts_comm_connect_local), batches of SNPs issued
+    from one host thread per engine, against the single-engine result and the oracle."""
+    import threading
+    import terastructure_b200 as ts
+    from terastructure_b200 import capi
+    if ts.lib().ts_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    c = load_case("synthB")
+    n, l, k = c["n"], c["l"], c["k"]
+    r = ts.Rng(c["seed"])
+    vl, vo, vi = r.sample_validation(n, l, c["rows"])
+    g0 = r.init_gamma(n, k)
+    o = ol.Oracle(c["y"], k, c["seed"])
+    locs = np.array([o.sample_loc() for _ in range(300)], np.uint32)
+    locs[10] = vl[0]
+    locs[12] = locs[11]
+    one = ts.Engine(n, l, k)
+    one.load_bed(c["rows"]); one.set_validation(vl, vo, vi); one.set_gamma(g0)
+    per = ((n + 1) // 2 + 3) // 4 * 4
+    sh = [ts.Engine(n, l, k, device=i, rank=i, nranks=2, n_begin=i * per, n_local=min(per, n - i * per)) for i in range(2)]
+    for i, e in enumerate(sh):
+        e.load_bed(c["rows"]); e.set_validation(vl, vo, vi); e.set_gamma(g0[i * per:i * per + e.n_local])
+    capi.connect_local(sh)
+    one.steps(locs)
+    res = [None, None]
+
+    def run(i):
+        for lo in range(0, len(locs), 100):       # three batches of 100 SNPs per engine
+            sh[i].steps(locs[lo:lo + 100])
+        sh[i].sync()
+        res[i] = sh[i].heldout_ll(False)
+    th = [threading.Thread(target=run, args=(i,)) for i in range(2)]
+    [t.start() for t in th]; [t.join() for t in th]
+    for x in locs:
+        o.train_loc(int(x))
+    s1, c1, p1 = one.heldout_ll(False)
+    _, a, cnt_o, per_o = o.heldout(first=False, per_locus=True)
+    np.testing.assert_array_equal(sh[0].get_lambda(), sh[1].get_lambda())   # bit-identical on all ranks
+    gs = np.concatenate([e.gamma for e in sh])
+    assert rel_err(gs, one.gamma) < 1e-11 and rel_err(gs, o.gamma) < TIGHT
+    assert rel_err(sh[0].get_lambda(), o.lam) < TIGHT
+    assert res[0][1] + res[1][1] == c1 == cnt_o
+    np.testing.assert_allclose(res[0][2] + res[1][2], per_o, rtol=1e-10, atol=1e-12)
