@@ -168,6 +168,23 @@ int ts_sync(ts_engine *e);
 int ts_comm_export(ts_engine *e, void *handle_out);
 int ts_comm_connect(ts_engine *e, const void *all_handles /* nranks x 64 bytes, rank order */);
 int ts_comm_connect_local(ts_engine **engines, int n);
+/* Symmetric-memory exchange, with NVLS (NVSwitch multicast) when available.  The caller owns one
+ * buffer of ts_comm_state_bytes() bytes per rank, each mapped on this engine's device:
+ * rank_ptrs[nranks] (rank order, own rank included) and, optionally, a multicast pointer that
+ * aliases the same offsets of ALL ranks' buffers (e.g. torch.distributed._symmetric_memory:
+ * empty() + rendezvous() give buffer_ptrs and multicast_ptr).  The engine's exchange state moves into
+ * its own buffer; with a multicast pointer the per-round exchange becomes an in-switch reduction
+ * (every CTA of every rank adds its words with multimem.red; TSGPU_XCHG=mcslot|slots select the
+ * other schemes for measurements).  Call it on every rank, then synchronise the ranks (a host
+ * barrier) before the first ts_steps.  total_ctas = sum of the ranks' CTA counts (ts_get_plan), or 0
+ * when all shards have this engine's geometry.  ts_comm_connect_local does all of this by itself for
+ * the engines of one process. */
+uint64_t ts_comm_state_bytes(void);
+/* Exchange scheme in use: 0 peer stores into slots, 1 NVLS multicast store into slots, 2 NVLS
+ * in-switch reduction (multimem.red from every CTA). */
+int ts_comm_mode(const ts_engine *e);
+int ts_comm_attach_symmetric(ts_engine *e, const void *const *rank_ptrs, void *multicast_ptr, uint64_t bytes,
+                             uint32_t total_ctas);
 
 /* Launch geometry the engine uses for a shard of n_local individuals on a device with num_sms SMs
  * (pure host arithmetic, no device needed): individuals per thread held in registers by the

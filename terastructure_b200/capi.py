@@ -59,6 +59,9 @@ EXPORTS = {
     "ts_comm_export": (_i, [_vp, _vp]),
     "ts_comm_connect": (_i, [_vp, _vp]),
     "ts_comm_connect_local": (_i, [C.POINTER(_vp), _i]),
+    "ts_comm_state_bytes": (_u64, []),
+    "ts_comm_mode": (_i, [_vp]),
+    "ts_comm_attach_symmetric": (_i, [_vp, C.POINTER(_vp), _vp, _u64, _u32]),
     "ts_plan_shard": (_i, [_u64, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "ts_get_plan": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "ts_launch_count": (_u64, [_vp]),
@@ -273,6 +276,16 @@ class Engine:
         check(lib().ts_sync(self._h))
 
     # ---- exchange / profiling ---------------------------------------------------------------
+    def attach_symmetric(self, rank_ptrs, multicast_ptr, nbytes, total_ctas=0):
+        """Symmetric exchange buffers (one per rank, mapped on this device) and an optional NVLS
+        multicast alias; barrier between this call and the first steps()."""
+        arr = (_vp * len(rank_ptrs))(*[int(p) for p in rank_ptrs])
+        check(lib().ts_comm_attach_symmetric(self._h, arr, _vp(int(multicast_ptr) or None), nbytes, total_ctas))
+
+    @property
+    def comm_mode(self):
+        return lib().ts_comm_mode(self._h)
+
     def comm_export(self):
         buf = C.create_string_buffer(TS_COMM_HANDLE_BYTES)
         check(lib().ts_comm_export(self._h, buf))

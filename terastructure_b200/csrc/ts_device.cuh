@@ -12,6 +12,12 @@
 // ------------------------------------------------------------------------------------------
 enum : uint32_t { ITEM_HOL = 1u, ITEM_FIRST = 2u };
 
+// Exchange of the per-round statistics between the ranks:
+//   SLOTS   CTA 0 stores the GPU's totals into its slot on every peer (unicast NVLink stores)
+//   MCSLOT  the same with ONE multicast store (NVLS): the switch replicates it to every GPU
+//   MCRED   no local stage: every CTA adds its words with multimem.red to every GPU's accumulators
+enum : int { XMODE_SLOTS = 0, XMODE_MCSLOT = 1, XMODE_MCRED = 2 };
+
 struct WorkItem {
   const unsigned char *col;  // packed column the E-step/gamma step read (bed row or vcol row)
   uint32_t loc;
@@ -88,6 +94,9 @@ struct Params {
   // persistent kernel
   PState *pst;
   PState *pst_peer[MAXR];
+  PState *pst_mc;                  // NVLS multicast alias of the symmetric PState (same offsets on all ranks), or null
+  int xmode;                       // XMODE_*: how the ranks' totals of a round are exchanged
+  unsigned long long mc_arrivals;  // XMODE_MCRED: CTAs per GPU x ranks = arrivals per word and round
   double fx_scale, fx_inv;  // 2^sh and 2^-sh of the fixed-point statistics
   int xflush;               // fence.sys after the peer stores (TSGPU_XFLUSH, default off)
   unsigned long long timeout_ns;  // wall-clock limit of one grid/peer wait (TSGPU_TIMEOUT_S, default 60 s)

@@ -31,6 +31,7 @@
 
 #include "ts_device.cuh"
 #include "ts_fixed.cuh"
+#include "ts_symm.hpp"
 
 // ------------------------------------------------------------------------------------------
 // error plumbing
@@ -441,8 +442,13 @@ struct ts_engine {
   Ctl *ctl = nullptr;
   WorkItem *items = nullptr;
   size_t items_cap = 0;
-  Xchg *xchg = nullptr;
-  Xbuf *xbuf = nullptr;  // &xchg->x
+  Xchg *xchg = nullptr;      // the exchange buffer in use: xchg_own, or this rank's part of a symmetric group
+  Xchg *xchg_own = nullptr;  // cudaMalloc'ed at creation (exported through CUDA IPC)
+  Xchg *xchg_mc = nullptr;   // NVLS multicast alias of the symmetric buffer, or null
+  Xbuf *xbuf = nullptr;      // &xchg->x
+  int xmode = XMODE_SLOTS;
+  unsigned long long mc_arrivals = 0;
+  SymmGroup *symm = nullptr; // owned by rank 0's engine of a ts_comm_connect_local group
   bool staged = false;   // TSGPU_PATH=staged: one launch per round (debug cross-check path)
   int grid_persist = 1, block_persist = 32, ind_per_thread = 1;
   std::vector<void *> ipc_opened;
@@ -499,6 +505,9 @@ static void fill_params(ts_engine *e) {
   p.nranks = e->cfg.nranks;
   p.xlocal = e->xbuf;
   p.pst = &e->xchg->ps;
+  p.pst_mc = e->xchg_mc ? &e->xchg_mc->ps : nullptr;
+  p.xmode = e->xmode;
+  p.mc_arrivals = e->mc_arrivals;
 }
 
 // K dispatch ---------------------------------------------------------------------------------
@@ -533,6 +542,33 @@ static void launch_heldout(ts_engine *e, unsigned n_items) {
 
 static cudaError_t launch_persist(ts_engine *e, uint32_t n_items) {
   return ts_launch_persist(e->K, e->ind_per_thread, e->prm, n_items, e->grid_persist, e->block_persist, e->stream);
+}
+
+// Move the engine's exchange state into rank_ptrs[rank] (one buffer per rank, all reachable from this
+// device) and pick the exchange mode.  The caller guarantees that no rank steps before all have attached.
+static int attach_symmetric(ts_engine *e, void *const *rank_ptrs, void *mc, unsigned long long total_ctas) {
+  if (use_device(e)) return TS_ERR_CUDA;
+  CK(cudaStreamSynchronize(e->stream));
+  Xchg *mine = (Xchg *)rank_ptrs[e->cfg.rank];
+  CK(cudaMemcpy(mine, e->xchg, sizeof(Xchg), cudaMemcpyDeviceToDevice));  // barrier history, round counter
+  CK(cudaDeviceSynchronize());
+  e->xchg = mine;
+  e->xbuf = &mine->x;
+  e->xchg_mc = (Xchg *)mc;
+  for (int r = 0; r < e->cfg.nranks; ++r) {
+    e->prm.xpeer[r] = &((Xchg *)rank_ptrs[r])->x;
+    e->prm.pst_peer[r] = &((Xchg *)rank_ptrs[r])->ps;
+  }
+  e->mc_arrivals = total_ctas;
+  const char *xm = getenv("TSGPU_XCHG");  // slots | mcslot | mcred (measurements: profiles/r2_summary.md)
+  int mode = mc ? XMODE_MCRED : XMODE_SLOTS;
+  if (xm && !strcmp(xm, "slots")) mode = XMODE_SLOTS;
+  else if (xm && !strcmp(xm, "mcslot") && mc) mode = XMODE_MCSLOT;
+  else if (xm && !strcmp(xm, "mcred") && mc) mode = XMODE_MCRED;
+  if (mode == XMODE_MCRED && total_ctas >= (1ull << (64 - tsfx::MC_CNT_SHIFT))) mode = XMODE_MCSLOT;  // arrival counter too narrow
+  e->xmode = mode;
+  fill_params(e);
+  return TS_OK;
 }
 
 extern "C" {
@@ -661,7 +697,8 @@ int ts_create(const ts_config *cfg, ts_engine **out) {
   CKE(dalloc(&e->cnt, e->npad));
   CKE(dalloc(&e->lambda, (size_t)cfg->l * K * 2));
   CKE(dalloc(&e->ctl, 1));
-  CKE(dalloc(&e->xchg, 1));
+  CKE(dalloc(&e->xchg_own, 1));
+  e->xchg = e->xchg_own;
   e->xbuf = &e->xchg->x;
   CKE(cudaMemsetAsync(e->gamma, 0, K * e->npad * sizeof(double), e->stream));
   CKE(cudaMemsetAsync(e->E, 0, K * e->npad * sizeof(double), e->stream));
@@ -729,7 +766,8 @@ int ts_destroy(ts_engine *e) {
   cudaFree(e->rounds);
   cudaFree(e->ctl);
   cudaFree(e->items);
-  cudaFree(e->xchg);
+  cudaFree(e->xchg_own);
+  symm_free(e->symm);
   cudaFree(e->prm.trace);
   cudaFree(e->d_voff);
   cudaFree(e->d_vind);
@@ -1057,7 +1095,8 @@ int ts_comm_export(ts_engine *e, void *handle_out) {
   if (use_device(e)) return TS_ERR_CUDA;
   static_assert(sizeof(cudaIpcMemHandle_t) == TS_COMM_HANDLE_BYTES, "IPC handle size");
   cudaIpcMemHandle_t h;
-  CK(cudaIpcGetMemHandle(&h, e->xchg));
+  if (e->xchg != e->xchg_own) return set_err(TS_ERR_STATE, "ts_comm_export: a symmetric buffer is already attached");
+  CK(cudaIpcGetMemHandle(&h, e->xchg_own));
   memcpy(handle_out, &h, sizeof h);
   return TS_OK;
 }
@@ -1104,7 +1143,44 @@ int ts_comm_connect_local(ts_engine **engines, int n) {
       e->prm.pst_peer[j] = &engines[j]->xchg->ps;
     }
   }
+  // Distinct devices: move the exchange state into symmetric buffers with an NVLS multicast alias when
+  // the fabric offers one (TSGPU_XCHG=slots keeps the plain peer-store exchange).
+  bool distinct = n > 1;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j)
+      if (engines[i]->cfg.device == engines[j]->cfg.device) distinct = false;
+  const char *xm = getenv("TSGPU_XCHG");
+  if (distinct && !(xm && !strcmp(xm, "slots")) && !engines[0]->symm) {
+    std::vector<int> devs(n);
+    for (int i = 0; i < n; ++i) devs[i] = engines[i]->cfg.device;
+    std::string err;
+    SymmGroup *g = symm_alloc_local(devs.data(), n, sizeof(Xchg), true, &err);
+    if (g && g->has_multicast()) {
+      unsigned long long ctas = 0;
+      for (int i = 0; i < n; ++i) ctas += (unsigned long long)engines[i]->grid_persist;
+      for (int i = 0; i < n; ++i) {
+        int rc = attach_symmetric(engines[i], g->uc.data(), g->mc[i], ctas);
+        if (rc) { symm_free(g); return rc; }
+      }
+      engines[0]->symm = g;
+    } else {
+      symm_free(g);  // no NVLS here: the peer-store exchange set up above stays
+    }
+  }
   return TS_OK;
+}
+
+uint64_t ts_comm_state_bytes(void) { return sizeof(Xchg); }
+int ts_comm_mode(const ts_engine *e) { return e ? e->xmode : -1; }
+
+int ts_comm_attach_symmetric(ts_engine *e, const void *const *rank_ptrs, void *multicast_ptr, uint64_t bytes, uint32_t total_ctas) {
+  if (!e || !rank_ptrs) return set_err(TS_ERR_ARG, "ts_comm_attach_symmetric: null argument");
+  if (bytes < sizeof(Xchg)) return set_err(TS_ERR_ARG, "ts_comm_attach_symmetric: %llu bytes, need %zu", (unsigned long long)bytes, sizeof(Xchg));
+  for (int r = 0; r < e->cfg.nranks; ++r)
+    if (!rank_ptrs[r] || ((uintptr_t)rank_ptrs[r] & 15)) return set_err(TS_ERR_ARG, "ts_comm_attach_symmetric: rank %d pointer null or not 16-byte aligned", r);
+  if ((uintptr_t)multicast_ptr & 15) return set_err(TS_ERR_ARG, "ts_comm_attach_symmetric: multicast pointer not 16-byte aligned");
+  return attach_symmetric(e, (void *const *)rank_ptrs, multicast_ptr,
+                          total_ctas ? total_ctas : (unsigned long long)e->grid_persist * e->cfg.nranks);
 }
 
 uint64_t ts_launch_count(const ts_engine *e) { return e ? e->launches : 0; }

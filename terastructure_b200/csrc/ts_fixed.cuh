@@ -76,6 +76,18 @@ TSFX_HD void fold(unsigned long long &hi, unsigned long long &lo) {
   lo &= (1ull << LO_BITS) - 1;
 }
 
+// In-switch (NVLS) exchange, XMODE_MCRED: every CTA of every GPU arrives on every word, up to
+// 8 x 148 = 1184 arrivals, so the count takes 11 bits (MC_CNT_SHIFT = 53) and the low word travels
+// as lo >> 2 (< 2^42 per CTA, < 2^52.3 in total: fits the 53 data bits; the two dropped bits are
+// 2^-42 of the high word's unit).  mc_unpack restores the (hi, lo) convention from the totals.
+constexpr int MC_CNT_SHIFT = 53;
+constexpr unsigned long long MC_MASK = (1ull << MC_CNT_SHIFT) - 1;
+constexpr int MC_LO_DROP = 2;
+TSFX_HD void mc_unpack(unsigned long long &hi, unsigned long long &lo) {
+  hi += lo >> (LO_BITS - MC_LO_DROP);
+  lo = (lo & ((1ull << (LO_BITS - MC_LO_DROP)) - 1)) << MC_LO_DROP;
+}
+
 // Totals (both words < 2^52) back to the statistic: (2^52 + d) * 2^-s - 2^(52-s) is exact, so each
 // word costs one integer OR and one DFMA; the sum of the two rounds once.
 struct Unscale {

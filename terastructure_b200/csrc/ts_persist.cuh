@@ -31,6 +31,18 @@
 #include "ts_expsi.cuh"
 #include "ts_fixed.cuh"
 
+// Build-time variants for A/B measurements (tools/dev/ab.sh builds one library per TS_OPTS value):
+//   bit 0  the gamma step has ONE call site (early-converged SNPs and hol items take one more loop trip
+//          for it): the kernel's instruction footprint shrinks by a third (instruction-cache misses)
+//   bit 1  one Newton step instead of two in the E-step's reciprocals (relative error < 1e-11 in a weight)
+//   bit 2  the next SNP's work item and genotype codes are loaded during the current SNP
+#ifndef TS_OPTS
+#define TS_OPTS 0
+#endif
+#define TS_OPT_SG ((TS_OPTS) & 1)
+#define TS_OPT_N1 ((TS_OPTS) & 2)
+#define TS_OPT_PRE ((TS_OPTS) & 4)
+
 namespace tsp {
 
 constexpr int FX_CNT_SHIFT = tsfx::CNT_SHIFT;
@@ -85,6 +97,16 @@ __device__ __forceinline__ void ld_pair_sys(const unsigned long long *p, unsigne
 }
 __device__ __forceinline__ void red_add(unsigned long long *p, unsigned long long v) {
   asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// NVLS (NVSwitch multicast): the operation is applied to every GPU's copy of the symmetric buffer.
+__device__ __forceinline__ void mm_red_add(unsigned long long *p, unsigned long long v) {
+  asm volatile("multimem.red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// 16-byte multicast store of a (hi, lo) pair; multimem.st has no .v2.u64 form, the bits travel as 4 x b32
+__device__ __forceinline__ void mm_st_pair(unsigned long long *p, unsigned long long a, unsigned long long b) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)a),
+               "r"((unsigned)(a >> 32)), "r"((unsigned)b), "r"((unsigned)(b >> 32))
+               : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -200,16 +222,39 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
   }
   __syncthreads();
 
+#if TS_OPT_PRE
+  WorkItem nxt = p.items[0];
+  unsigned ncode = 0;      // the next SNP's codes of this thread's individuals, 2 bits each
+  bool have_ncode = false;
+#endif
   for (uint32_t i = 0; i < n_items; ++i) {
+#if TS_OPT_PRE
+    const WorkItem it = nxt;
+#else
     const WorkItem it = p.items[i];
+#endif
     const unsigned char *col = it.col;
     int code[IR];
     if constexpr (I > 0) {
+#if TS_OPT_PRE
+      if (have_ncode) {
 #pragma unroll
-      for (int j = 0; j < I; ++j) code[j] = valid[j] ? tsm::plink_code(col, nj[j]) : 1;
+        for (int j = 0; j < I; ++j) code[j] = (ncode >> (2 * j)) & 3;
+      } else
+#endif
+      {
+#pragma unroll
+        for (int j = 0; j < I; ++j) code[j] = valid[j] ? tsm::plink_code(col, nj[j]) : 1;
+      }
     }
+#if TS_OPT_PRE
+    have_ncode = false;
+#endif
     if (i + 1 < n_items) {  // next SNP's genotype column and lambda row -> L2
       const WorkItem nx = p.items[i + 1];
+#if TS_OPT_PRE
+      nxt = nx;
+#endif
       if constexpr (I > 0) {
 #pragma unroll
         for (int j = 0; j < I; ++j)
@@ -353,8 +398,23 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
         }
       }
     };
+    bool tail = false;          // TS_OPT_SG: a last loop trip that only runs the gamma step
+    const double *bg = nullptr;  // the b the gamma step uses (the last executed E-step's)
     while (true) {
       const double *bx = x == 0 ? b_first : s_b + (x & 1) * V;
+      const int par = (int)(rc & 1);
+      bool gamma_now = tail;
+      if (!tail) {
+#if TS_OPT_PRE
+      if constexpr (I > 0) {
+        if (x == 1 && i + 1 < n_items) {  // the loads complete behind this round; consumed at the next SNP
+          ncode = 0;
+#pragma unroll
+          for (int j = 0; j < I; ++j) ncode |= (unsigned)(valid[j] ? tsm::plink_code(nxt.col, nj[j]) : 1) << (2 * j);
+          have_ncode = true;
+        }
+      }
+#endif
       // ---- E-step over this thread's individuals: registers + broadcast shared-memory b --------
       double vv[V];
 #pragma unroll
@@ -371,8 +431,13 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
           s1 = fma(en[k], bk.y, s1);
         }
         // padding threads (no individual) have e = 0, s = 0: keep the reciprocal finite
+#if TS_OPT_N1
+        q0 = w0 * fast_rcp1(ok ? s0 : 1.0);
+        q1 = w1 * fast_rcp1(ok ? s1 : 1.0);
+#else
         q0 = w0 * fast_rcp(ok ? s0 : 1.0);
         q1 = w1 * fast_rcp(ok ? s1 : 1.0);
+#endif
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           vv[2 * k] = fma(en[k], q0, vv[2 * k]);
@@ -409,7 +474,6 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
       TS_TRACE(2 + 8 * x + 1);
       __syncthreads();
       TS_TRACE(2 + 8 * x + 2);
-      const int par = (int)(rc & 1);
       for (int v = tid; v < V; v += blockDim.x) {  // add the warps' words, publish with arrival count 1
         const long long *sh = s_fix + v * WS, *sl = s_fix + (V + v) * WS;
         long long hi = 0, lo = 0;
@@ -420,18 +484,26 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
         // row hand-off: these lanes of CTA 0 stored the previous SNP's row; by now that store has
         // long been performed, so the fence that orders it before this arrival waits for nothing
         if (x == 0 && blockIdx.x == 0) fence_gpu();
-        red_add(&st->acc[par][v][0], (unsigned long long)hi + (1ull << FX_CNT_SHIFT));
-        red_add(&st->acc[par][V + v][0], (unsigned long long)lo + (1ull << FX_CNT_SHIFT));
+        if (p.xmode == XMODE_MCRED) {  // in-switch: one arrival per CTA on EVERY GPU's copy of the word
+          mm_red_add(&p.pst_mc->acc[par][v][0], (unsigned long long)hi + (1ull << tsfx::MC_CNT_SHIFT));
+          mm_red_add(&p.pst_mc->acc[par][V + v][0], ((unsigned long long)lo >> tsfx::MC_LO_DROP) + (1ull << tsfx::MC_CNT_SHIFT));
+        } else {
+          red_add(&st->acc[par][v][0], (unsigned long long)hi + (1ull << FX_CNT_SHIFT));
+          red_add(&st->acc[par][V + v][0], (unsigned long long)lo + (1ull << FX_CNT_SHIFT));
+        }
       }
       TS_TRACE(2 + 8 * x + 3);
       // The last round's totals only feed lambda[loc] (the gamma step uses the phi of THIS E-step),
       // so when this round is known to be the last one the gamma step runs now, in the shadow of
       // the grid barrier, and the control warp collects the totals afterwards.
-      if (x + 1 >= p.max_rounds && !(it.flags & ITEM_HOL)) {
+      if (x + 1 >= p.max_rounds && !(it.flags & ITEM_HOL)) { gamma_now = true; bg = bx; }
+      }  // !tail
+      if (gamma_now) {
         prepare_next();
-        gamma_step(bx);
+        if (!(it.flags & ITEM_HOL)) gamma_step(bg);
         gamma_done = true;
       }
+      if (tail) break;
       // ---- control warp: grid barrier + totals, lambda update, convergence, new b -------------
       if (warp == 0) {
         __syncwarp();  // the gamma step above has lane-dependent control flow
@@ -446,7 +518,21 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
             // single GPU: every CTA waits for the local words.  Several GPUs: only CTA 0 does (it
             // forwards the GPU's totals); the other CTAs wait for the rank slots alone, which keeps
             // the pollers off the words the arrivals are being added to.
-            if (p.nranks == 1 || blockIdx.x == 0) {
+            if (p.xmode == XMODE_MCRED) {
+              // every CTA of every rank arrived on this GPU's copy: the single-GPU wait with a wider
+              // count (ranks x CTAs) and the packed low word
+              const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q];
+              while (true) {
+                dh = ld_relaxed_sys(&st->acc[par][v][0]) - bh;
+                dl = ld_relaxed_sys(&st->acc[par][V + v][0]) - bl;
+                if ((dh >> tsfx::MC_CNT_SHIFT) == p.mc_arrivals && (dl >> tsfx::MC_CNT_SHIFT) == p.mc_arrivals) break;
+                if (guard.expired(p.timeout_ns)) { abort = true; break; }
+              }
+              if (par) { ph1[q] = bh + dh; pl1[q] = bl + dl; } else { ph0[q] = bh + dh; pl0[q] = bl + dl; }
+              dh &= tsfx::MC_MASK;
+              dl &= tsfx::MC_MASK;
+              tsfx::mc_unpack(dh, dl);
+            } else if (p.nranks == 1 || blockIdx.x == 0) {
               const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q];
               while (true) {
                 dh = ld_relaxed(&st->acc[par][v][0]) - bh;
@@ -459,10 +545,11 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
               dl &= FX_MASK;
               if (q == 0) TS_TRACE(82 + 2 * x);  // local words complete
             }
-            if (p.nranks > 1) {
+            if (p.nranks > 1 && p.xmode != XMODE_MCRED) {
               const unsigned long long tag = ((rc + 1) & 1023ull) << FX_CNT_SHIFT;
               if (blockIdx.x == 0) {
-                for (int r = 0; r < p.nranks; ++r) st_pair_sys(&p.pst_peer[r]->slot[p.rank][par][v][0], tag | dh, tag | dl);
+                if (p.xmode == XMODE_MCSLOT) mm_st_pair(&p.pst_mc->slot[p.rank][par][v][0], tag | dh, tag | dl);  // one store, the switch replicates it
+                else for (int r = 0; r < p.nranks; ++r) st_pair_sys(&p.pst_peer[r]->slot[p.rank][par][v][0], tag | dh, tag | dl);
                 if (p.xflush) __threadfence_system();  // push the NVLink writes out now
                 if (q == 0) TS_TRACE(83 + 2 * x);  // peer stores issued
               }
@@ -554,15 +641,25 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
       ++rc;
       const int flag = *s_flag;
       if (flag & 2) return;
+#if TS_OPT_SG
+      if (flag & 1) {
+        if (gamma_done) break;
+        tail = true;  // early-converged SNPs and hol items: one more trip for the gamma step / the helper
+        bg = x == 1 ? b_first : s_b + ((x - 1) & 1) * V;
+      }
+#else
       if (flag & 1) break;
+#endif
     }
 
     // early-converged SNPs take the gamma step here; the usual case (all rounds run) took it
     // inside the last round, in the shadow of that round's grid barrier
+#if !TS_OPT_SG
     if (!gamma_done) {
       prepare_next();
       if (!(it.flags & ITEM_HOL)) gamma_step(x == 1 ? b_first : s_b + ((x - 1) & 1) * V);
     }
+#endif
     TS_TRACE(100);
     __syncthreads();  // s_b is rewritten for the next SNP
     TS_TRACE(101);

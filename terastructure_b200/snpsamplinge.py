@@ -49,7 +49,8 @@ class SNPSamplingE:
     Multi-GPU: pass this rank's shard (rank, nranks, device) and an `allgather(obj)->list`
     callable; every rank runs the same host loop on the same RNG stream."""
 
-    def __init__(self, env, bed_rows, *, device=0, rank=0, nranks=1, allgather=None, gamma0=None, engine=None):
+    def __init__(self, env, bed_rows, *, device=0, rank=0, nranks=1, allgather=None, gamma0=None, engine=None,
+                 connect=True):
         self.env = env
         self._n, self._k, self._l = env.n, env.k, env.l
         self._iter = 0
@@ -86,7 +87,7 @@ class SNPSamplingE:
                                       online_iterations=env.online_iterations)
             self.engine.load_bed(bed_rows)
         self.engine.set_validation(self.val_loc, self.val_off, self.val_indiv)
-        if nranks > 1:
+        if nranks > 1 and connect:  # connect=False: the caller wired the exchange already (dist.connect)
             handles = allgather(self.engine.comm_export())
             self.engine.comm_connect(handles)
 
@@ -180,12 +181,13 @@ class SNPSamplingE:
     def gather_theta(self):
         return self._gather(self.engine.theta)
 
-    def infer(self, max_iter=None):
+    def infer(self, max_iter=None, max_seconds=None):
         """cc:417-459.  The reference never returns (exit(0) from compute_likelihood); here the
-        loop returns when the stopping rule fires, on env.terminate, or after max_iter
-        iterations (tests).  SNP indices are pre-drawn up to the next report: in steady state
+        loop returns when the stopping rule fires, on env.terminate, after max_iter
+        iterations (tests) or at the first report after max_seconds (benchmarks).  SNP indices are pre-drawn up to the next report: in steady state
         the RNG is consumed by SNP sampling only, so the stream is unchanged."""
         rf = self.env.reportfreq
+        t_begin = time.time()
         while not self.stopped:
             m = rf - self._iter % rf
             if max_iter is not None:
@@ -199,6 +201,12 @@ class SNPSamplingE:
                 if self.compute_likelihood(False, True):
                     break
                 self.save_model()
+                if max_seconds is not None:  # benchmarks: give up at a report boundary, all ranks together
+                    over = time.time() - t_begin > max_seconds
+                    if self.nranks > 1:
+                        over = self._allgather(over)[0]
+                    if over:
+                        break
             if self.env.terminate:
                 self.save_model()
                 break
