@@ -88,6 +88,12 @@ int ts_destroy(ts_engine *e);
  * 2-bit packed in HBM (codes 00->0, 10->1, 11->2, 01->missing, snp.cc:203-216). */
 int ts_load_bed(ts_engine *e, uint64_t loc_begin, uint64_t nloc, const uint8_t *rows,
                 uint64_t row_pitch);
+/* The same for all engines of one process in ONE pass over the rows (the CLI's -gpus N; rows is
+ * typically a memory-mapped .bed of up to 250 GB): chunks are staged through pinned host buffers and
+ * every engine copies its own byte range asynchronously while the next chunk is read.  Returns when
+ * all engines hold their shards. */
+int ts_load_bed_fanout(ts_engine **engines, int n, uint64_t loc_begin, uint64_t nloc, const uint8_t *rows,
+                       uint64_t row_pitch);
 /* Synthetic genotypes generated on the device (BASELINE.md section 4 / SURVEY.md 8d):
  * y[l][n] ~ Binomial(2, sum_k theta[n][k]*beta[l][k]) from a counter-based generator keyed
  * by (seed, l, global n); `missing_rate` of the entries become the missing code.

@@ -40,6 +40,7 @@ EXPORTS = {
     "ts_create": (_i, [C.POINTER(TsConfig), C.POINTER(_vp)]),
     "ts_destroy": (_i, [_vp]),
     "ts_load_bed": (_i, [_vp, _u64, _u64, _vp, _u64]),
+    "ts_load_bed_fanout": (_i, [C.POINTER(_vp), _i, _u64, _u64, _vp, _u64]),
     "ts_synth_bed": (_i, [_vp, _u64, _vp, _vp, _d]),
     "ts_get_bed_row": (_i, [_vp, _u64, _vp]),
     "ts_set_validation": (_i, [_vp, _u64, _vp, _vp, _vp]),
@@ -319,6 +320,13 @@ class Engine:
         ms = C.c_float()
         check(lib().ts_timer_stop(self._h, C.byref(ms)))
         return ms.value
+
+
+def load_bed_fanout(engines, rows, loc_begin=0):
+    """One pass over `rows` ([nloc, >= ceil(N/4)] packed, e.g. a np.memmap of a .bed) for all engines."""
+    assert rows.ndim == 2 and rows.dtype == np.uint8 and rows.strides[1] == 1
+    arr = (_vp * len(engines))(*[e._h for e in engines])
+    check(lib().ts_load_bed_fanout(arr, len(engines), loc_begin, rows.shape[0], rows.ctypes.data, rows.strides[0]))
 
 
 def connect_local(engines):

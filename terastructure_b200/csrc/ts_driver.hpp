@@ -299,23 +299,27 @@ class SNPSamplingE {
 
   // cc:417-459.  SNP indices are drawn on the host from the reference's RNG stream, in
   // batches that end at the next report; the engine runs a batch without host round trips.
+  // The reference prints a progress line every 100 iterations (cc:436-439); the lines of a batch
+  // are printed when the batch has completed (same text, the seconds are the batch's).
+  // SIGTERM (main.cc:28-39) is honoured at batch boundaries (at most `chunk_max` iterations later;
+  // the reference: after the current iteration, before the pending lazy gamma step -- here the
+  // gamma step of the last SNP has been applied, which SURVEY App. A note 3 allows).
   void infer() {
     const uint32_t chunk_max = 1u << 15;
     std::vector<uint32_t> locs;
     while (1) {
       const uint32_t to_report = _env.reportfreq - _iter % _env.reportfreq;
-      const uint32_t to_progress = 100 - _iter % 100;
-      uint32_t m = std::min(std::min(to_report, chunk_max), std::max(to_progress, 100u * ((to_report) / 100u)));
-      if (m == 0) m = to_progress;
+      const uint32_t m = std::min(to_report, chunk_max);
       locs.resize(m);
       ts_rng_sample_locs(_r, _l, locs.data(), m);
-      for_each_engine([&](size_t r) { TSD_CHECK(ts_steps(_eng[r], locs.data(), m, 0, nullptr)); });
+      for_each_engine([&](size_t r) {
+        TSD_CHECK(ts_steps(_eng[r], locs.data(), m, 0, nullptr));
+        TSD_CHECK(ts_sync(_eng[r]));
+      });
+      const uint32_t before = _iter;
       _iter += m;
-      if (_iter % 100 == 0) {
-        for_each_engine([&](size_t r) { TSD_CHECK(ts_sync(_eng[r])); });
-        printf("\riteration = %d took %d secs", _iter, duration());
-        fflush(stdout);
-      }
+      for (uint32_t it = (before / 100 + 1) * 100; it <= _iter; it += 100) printf("\riteration = %d took %d secs", it, duration());
+      fflush(stdout);
       if (_iter % _env.reportfreq == 0) {
         printf("iteration = %d took %d secs\n", _iter, duration());
         _env.lerr("iteration = %d took %d secs\n", _iter, duration());
@@ -348,9 +352,15 @@ class SNPSamplingE {
   }
 
   void create_engines() {
-    const int ng = _env.ngpus;
-    uint64_t per = ((uint64_t)_n + ng - 1) / ng;
-    per = (per + 3) / 4 * 4;
+    int ng = _env.ngpus;
+    auto per_of = [&](int g) { return (((uint64_t)_n + g - 1) / g + 3) / 4 * 4; };
+    // every shard needs at least one individual (shard boundaries are multiples of 4)
+    while (ng > 1 && (uint64_t)(ng - 1) * per_of(ng) >= _n) ng--;
+    if (ng != _env.ngpus) {
+      fprintf(stderr, "+ -gpus %d leaves a GPU without individuals at n = %u; using %d\n", _env.ngpus, _n, ng);
+      _env.ngpus = ng;
+    }
+    const uint64_t per = per_of(ng);
     for (int r = 0; r < ng; ++r) {
       ts_config cfg;
       ts_config_defaults(&cfg, _n, _l, _k);
@@ -366,14 +376,12 @@ class SNPSamplingE {
       _eng.push_back(e);
       _begin.push_back(cfg.n_begin);
       _local.push_back(cfg.n_local);
-      // stream the shard's bytes to the device in chunks of loci (the source may be a mapped file)
-      const uint64_t chunk = std::max<uint64_t>(1, (256ull << 20) / _snp.bps);
-      for (uint64_t lo = 0; lo < _l; lo += chunk) {
-        const uint64_t m = std::min<uint64_t>(chunk, _l - lo);
-        TSD_CHECK(ts_load_bed(e, lo, m, _snp.rows + lo * _snp.bps, _snp.bps));
-      }
-      TSD_CHECK(ts_set_validation(e, _nval, _val_loc, _val_off, _val_indiv));
     }
+    // read_bed's payload loop (snp.cc:186-229): ONE pass over the (memory-mapped) rows, every GPU takes its bytes
+    const time_t t0 = time(0);
+    TSD_CHECK(ts_load_bed_fanout(_eng.data(), ng, 0, _l, _snp.rows, _snp.bps));
+    fprintf(stderr, "+ genotypes resident on %d GPU(s) after %d secs\n", ng, (int)(time(0) - t0));
+    for (int r = 0; r < ng; ++r) TSD_CHECK(ts_set_validation(_eng[r], _nval, _val_loc, _val_off, _val_indiv));
     if (ng > 1) TSD_CHECK(ts_comm_connect_local(_eng.data(), ng));
   }
 
@@ -407,6 +415,7 @@ class SNPSamplingE {
       run_heldout_multi(first, per, k);
     }
     if (!first) _iter += (uint32_t)_nval;  // snp_likelihood: _iter++ per locus (hh:333)
+    for (uint64_t v = 0; v < _nval; ++v) printf("\rdone:%.2f%%", ((double)v / _nval) * 100);  // cc:494
     double s = 0.0;
     for (uint64_t v = 0; v < _nval; ++v) s += per[v];
     const double a = s / k;
@@ -520,8 +529,10 @@ class SNPSamplingE {
         TSD_CHECK(ts_steps(_eng[r], locs.data() + off, m, 0, nullptr));
         TSD_CHECK(ts_sync(_eng[r]));
       });
-      _iter += (uint32_t)m;
-      printf("\rloc = %d took %d secs", _iter, duration());
+      for (size_t j = 0; j < m; ++j) {  // cc:376-379 / :405-408
+        _iter++;
+        if (locs[off + j] % 100 == 0) printf("\rloc = %d took %d secs", _iter, duration());
+      }
       fflush(stdout);
     }
   }
@@ -534,15 +545,22 @@ class SNPSamplingE {
 
   void compute_and_save_beta() {  // cc:384-413
     _env.lerr("within compute_and_save_beta()");
-    std::ifstream in(_env.locations_file);
+    // File grammar of the reference (cc:389-397): records "<loc><TAB><rest of line>", read with
+    // fscanf("%d\t%*[^\n]s\n").  The conversion is kept as it is there, quirks included: the
+    // white-space directive after %d also eats a newline, so in a file with bare numbers (no second
+    // column) every other line is swallowed as the "rest of line" -- the reference behaves the same.
+    FILE *lf = fopen(_env.locations_file.c_str(), "r");
+    if (!lf) { _env.lerr("cannot open locations file:%s\n", strerror(errno)); exit(-1); }
     std::vector<uint32_t> locs;
-    std::string line;
-    while (std::getline(in, line)) {
-      if (line.empty()) continue;
-      const long v = strtol(line.c_str(), nullptr, 10);
-      if (v < 0 || (uint32_t)v >= _l) { fprintf(stderr, "bad location %ld in %s\n", v, _env.locations_file.c_str()); exit(-1); }
-      locs.push_back((uint32_t)v);
+    int v = 0;
+    while (!feof(lf)) {
+      if (fscanf(lf, "%d\t%*[^\n]s\n", &v) >= 0) {
+        if (v < 0 || (uint32_t)v >= _l) { fprintf(stderr, "bad location %d in %s\n", v, _env.locations_file.c_str()); exit(-1); }
+        _env.lerr("loc = %d", v);
+        locs.push_back((uint32_t)v);
+      }
     }
+    fclose(lf);
     _env.lerr("locs size = %d", (int)locs.size());
     sweep(locs);
     save_beta(&locs);

@@ -27,6 +27,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ts_device.cuh"
@@ -793,6 +794,74 @@ int ts_load_bed(ts_engine *e, uint64_t loc_begin, uint64_t nloc, const uint8_t *
   CK(cudaStreamSynchronize(e->stream));
   e->bed_loaded = true;
   return TS_OK;
+}
+
+// One pass over the rows for ALL engines of a process (the CLI's -gpus N): rows are staged through two
+// pinned host buffers (the source is usually a memory-mapped .bed: copying it into the staging buffer
+// is what reads the file, done by a few host threads), and every engine pulls its byte range of the
+// staged chunk with an asynchronous 2-D copy while the next chunk is being read.
+int ts_load_bed_fanout(ts_engine **engines, int n, uint64_t loc_begin, uint64_t nloc, const uint8_t *rows,
+                       uint64_t row_pitch) {
+  if (!engines || n < 1 || !rows) return set_err(TS_ERR_ARG, "ts_load_bed_fanout: null argument");
+  const ts_engine *e0 = engines[0];
+  const size_t full_bytes = (e0->cfg.n_total + 3) / 4;
+  if (row_pitch < full_bytes) return set_err(TS_ERR_ARG, "ts_load_bed_fanout: row_pitch < ceil(N/4)");
+  for (int i = 0; i < n; ++i)
+    if (!engines[i] || engines[i]->cfg.n_total != e0->cfg.n_total || engines[i]->cfg.l != e0->cfg.l || loc_begin + nloc > engines[i]->cfg.l)
+      return set_err(TS_ERR_ARG, "ts_load_bed_fanout: engines disagree on the data set shape, or loci out of range");
+  if (nloc == 0) return TS_OK;
+  const size_t spitch = (full_bytes + 15) / 16 * 16;
+  const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(nloc, (128ull << 20) / spitch));
+  uint8_t *stage[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> done[2];
+  int rc = TS_OK;
+  auto fail = [&](const char *what, cudaError_t er) { rc = set_err(TS_ERR_CUDA, "ts_load_bed_fanout: %s: %s", what, cudaGetErrorString(er)); };
+  for (int b = 0; b < 2 && rc == TS_OK; ++b) {
+    cudaError_t er = cudaHostAlloc((void **)&stage[b], chunk * spitch, cudaHostAllocPortable);
+    if (er != cudaSuccess) { fail("cudaHostAlloc", er); break; }
+    done[b].resize(n);
+    for (int i = 0; i < n; ++i) {
+      cudaSetDevice(engines[i]->cfg.device);
+      if ((er = cudaEventCreateWithFlags(&done[b][i], cudaEventDisableTiming)) != cudaSuccess) { fail("cudaEventCreate", er); break; }
+    }
+  }
+  const unsigned nthreads = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+  uint64_t c = 0;
+  for (uint64_t lo = 0; lo < nloc && rc == TS_OK; lo += chunk, ++c) {
+    const uint64_t m = std::min<uint64_t>(chunk, nloc - lo);
+    const int b = (int)(c & 1);
+    if (c >= 2)
+      for (int i = 0; i < n; ++i) cudaEventSynchronize(done[b][i]);  // the copies that read this buffer two chunks ago
+    {  // file -> pinned staging, rows split over host threads
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nthreads; ++t)
+        th.emplace_back([&, t] {
+          for (uint64_t r = t; r < m; r += nthreads) memcpy(stage[b] + r * spitch, rows + (loc_begin + lo + r) * row_pitch, full_bytes);
+        });
+      for (auto &x : th) x.join();
+    }
+    for (int i = 0; i < n && rc == TS_OK; ++i) {
+      ts_engine *e = engines[i];
+      cudaError_t er = cudaSetDevice(e->cfg.device);
+      unsigned char *dst = e->bed + (loc_begin + lo) * e->pitch;
+      if (er == cudaSuccess && e->pitch != e->local_bytes) er = cudaMemset2DAsync(dst, e->pitch, 0, e->pitch, m, e->stream);
+      if (er == cudaSuccess)
+        er = cudaMemcpy2DAsync(dst, e->pitch, stage[b] + e->cfg.n_begin / 4, spitch, e->local_bytes, m, cudaMemcpyHostToDevice, e->stream);
+      if (er == cudaSuccess) er = cudaEventRecord(done[b][i], e->stream);
+      if (er != cudaSuccess) fail("upload", er);
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    cudaSetDevice(engines[i]->cfg.device);
+    cudaError_t er = cudaStreamSynchronize(engines[i]->stream);
+    if (er != cudaSuccess && rc == TS_OK) fail("cudaStreamSynchronize", er);
+    if (rc == TS_OK && loc_begin + nloc > 0) engines[i]->bed_loaded = true;
+  }
+  for (int b = 0; b < 2; ++b) {
+    for (size_t i = 0; i < done[b].size(); ++i) cudaEventDestroy(done[b][i]);
+    if (stage[b]) cudaFreeHost(stage[b]);
+  }
+  return rc;
 }
 
 int ts_synth_bed(ts_engine *e, uint64_t seed, const float *theta, const float *beta, double missing_rate) {

@@ -31,17 +31,13 @@
 #include "ts_expsi.cuh"
 #include "ts_fixed.cuh"
 
-// Build-time variants for A/B measurements (tools/dev/ab.sh builds one library per TS_OPTS value):
-//   bit 0  the gamma step has ONE call site (early-converged SNPs and hol items take one more loop trip
-//          for it): the kernel's instruction footprint shrinks by a third (instruction-cache misses)
-//   bit 1  one Newton step instead of two in the E-step's reciprocals (relative error < 1e-11 in a weight)
-//   bit 2  the next SNP's work item and genotype codes are loaded during the current SNP
+// Build-time switch for measurements (make lib SUFFIX=_nofence OPTS=8): bit 3 drops the fences of the
+// row hand-off (see "row hand-off" below) to price them.  Variants measured and rejected in round 2
+// (profiles/r2_summary.md): one gamma call site, preloading the next SNP's genotype codes.
 #ifndef TS_OPTS
 #define TS_OPTS 0
 #endif
-#define TS_OPT_SG ((TS_OPTS) & 1)
-#define TS_OPT_N1 ((TS_OPTS) & 2)
-#define TS_OPT_PRE ((TS_OPTS) & 4)
+#define TS_OPT_NOFENCE ((TS_OPTS) & 8)
 
 namespace tsp {
 
@@ -122,19 +118,24 @@ __device__ __forceinline__ double ld_row(const double *p) {
 __device__ __forceinline__ void st_row(double *p, double v) {
   asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
-__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_gpu() {
+#if !TS_OPT_NOFENCE
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Poll loops give up after Params::timeout_ns of WALL CLOCK (a lost CTA or rank), checked every 4096
-// polls so that the timer read stays off the fast path.
+// Poll loops give up after Params::timeout_ns of WALL CLOCK (a lost CTA or rank).  The timer is read
+// once per POLL_BURST polls, OUTSIDE the burst loop: the burst itself must stay as tight as the
+// round-1 loop (two loads, a compare, a branch; ptxas unrolls it) -- a guard inside it cost 500
+// cycles per round (gpurun_out/r2c1_trace.txt).
+constexpr int POLL_BURST = 4096;
 struct SpinGuard {
   unsigned long long t0 = 0;
-  unsigned spins = 0;
   __device__ __forceinline__ bool expired(unsigned long long limit_ns) {
-    if ((++spins & 4095u) != 0) return false;
     const unsigned long long now = global_ns();
     if (t0 == 0) { t0 = now; return false; }
     return now - t0 > limit_ns;
@@ -147,6 +148,16 @@ struct SpinGuard {
     if (p.trace && blockIdx.x == 0 && tid == 0 && i < 64 && (unsigned)(slot) < 128u)          \
       p.trace[(size_t)i * 128 + (slot)] = clock64();                                          \
   } while (0)
+
+// Row hand-off inside a launch.  The converged lambda row of a locus is needed again when the locus
+// is revisited (round-0 b, the convergence test's old lambda).  Every CTA forms that row itself, so
+// each keeps the rows of the last RING finished SNPs in shared memory and reads revisits within that
+// window from there.  Older rows come from global memory, where CTA 0 publishes every row with a
+// strong store and fences once every RING / 2 SNPs before a barrier arrival: a row that has left the
+// ring was stored more than RING SNPs ago, so a fence and at least RING / 2 grid barriers lie
+// between its store and any global read of it (release on the writer side; the readers fence before
+// the strong loads).  Price of the fence on CTA 0's path: ~950 cycles, once per RING / 2 SNPs.
+constexpr int RING = 8;
 
 // I >= 1: I individuals per thread live in registers; threads per CTA are capped so that the
 // register file holds them.  I == 0: streaming variant for shards beyond that capacity -- every
@@ -161,8 +172,9 @@ __host__ __device__ constexpr int persist_tmax(int K, int I) {
                  : (K <= 20 ? (I == 1 ? 384 : (I == 2 ? 256 : (I == 3 ? 224 : 192))) : 256);
 }
 __host__ __device__ constexpr size_t persist_smem_bytes(int K, int I) {
-  return sizeof(double) * (12 * K) + sizeof(long long) * (4 * K * (persist_tmax(K, I) / 32 + 1)) + 16;
+  return sizeof(double) * ((12 + 2 * RING) * K) + sizeof(uint32_t) * RING + sizeof(long long) * (4 * K * (persist_tmax(K, I) / 32 + 1)) + 16;
 }
+
 
 template <int K, int I>
 __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uint32_t n_items) {
@@ -174,8 +186,10 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
   double *s_b = reinterpret_cast<double *>(smem_raw);                // [2][V]: b of round x >= 1 at [x&1]
   double *s_b0 = s_b + 2 * V;                                        // [2][V]: b of round 0 of SNP i at [i&1]
   double *s_row0 = s_b0 + 2 * V;                                     // [2][V]: the lambda row that b came from
-  long long *s_fix = reinterpret_cast<long long *>(s_row0 + 2 * V);  // [NW][WS] per-warp fixed-point words
+  double *s_ring = s_row0 + 2 * V;                                   // [RING][V]: rows of the loci finished last
+  long long *s_fix = reinterpret_cast<long long *>(s_ring + RING * V);  // [NW][WS] per-warp fixed-point words
   int *s_flag = reinterpret_cast<int *>(s_fix + NW * WS);  // bit 0: round loop done, bit 1: abort
+  uint32_t *s_ring_loc = reinterpret_cast<uint32_t *>(s_flag + 4);  // [RING]: locus of a ring slot, ~0 = empty
 
   PState *st = p.pst;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
@@ -205,6 +219,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
     }
   }
   uint32_t prev_loc = 0xffffffffu;
+  if (tid < RING) s_ring_loc[tid] = 0xffffffffu;
 
   // this thread's individuals and their E = exp(psi(gamma)) rows, register-resident (I >= 1)
   constexpr int IR = I > 0 ? I : 1;
@@ -222,39 +237,18 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
   }
   __syncthreads();
 
-#if TS_OPT_PRE
-  WorkItem nxt = p.items[0];
-  unsigned ncode = 0;      // the next SNP's codes of this thread's individuals, 2 bits each
-  bool have_ncode = false;
-#endif
   for (uint32_t i = 0; i < n_items; ++i) {
-#if TS_OPT_PRE
-    const WorkItem it = nxt;
-#else
     const WorkItem it = p.items[i];
-#endif
     const unsigned char *col = it.col;
     int code[IR];
     if constexpr (I > 0) {
-#if TS_OPT_PRE
-      if (have_ncode) {
-#pragma unroll
-        for (int j = 0; j < I; ++j) code[j] = (ncode >> (2 * j)) & 3;
-      } else
-#endif
       {
 #pragma unroll
         for (int j = 0; j < I; ++j) code[j] = valid[j] ? tsm::plink_code(col, nj[j]) : 1;
       }
     }
-#if TS_OPT_PRE
-    have_ncode = false;
-#endif
     if (i + 1 < n_items) {  // next SNP's genotype column and lambda row -> L2
       const WorkItem nx = p.items[i + 1];
-#if TS_OPT_PRE
-      nxt = nx;
-#endif
       if constexpr (I > 0) {
 #pragma unroll
         for (int j = 0; j < I; ++j)
@@ -268,19 +262,23 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
     // prepared it while the previous SNP's gamma step ran, unless this is the launch's first SNP or
     // the same locus again (its row was not final then): the control warp does it here in that case.
     //
-    // Row hand-off inside a launch: CTA 0 publishes a locus' converged row (st_row) and fences before
-    // its next arrival on the grid barrier (see the publish step); a CTA reads the row of a locus
-    // only after it has passed that barrier, with strong loads behind a fence.  With a single
-    // permitted round the helper would run BEFORE this SNP's only barrier, i.e. possibly before CTA 0
-    // has stored the row of the SNP before it (locus sequence A, B, A): no preparation then.
+    // With a single permitted round the helper would run BEFORE this SNP's only barrier and before
+    // the previous SNP's row exists anywhere (locus sequence A, B, A): no preparation then.
+    auto load_row = [&](uint32_t loc, double (&own)[VPL]) {  // whole warp: ring first, global memory otherwise
+      const unsigned hit = __ballot_sync(0xffffffffu, lane < RING && s_ring_loc[lane] == loc);
+      if (hit) {
+        const double *row = s_ring + (__ffs(hit) - 1) * V;
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) own[q] = (lane + 32 * q < V) ? row[lane + 32 * q] : 1024.0;
+      } else {
+        fence_gpu();
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) own[q] = (lane + 32 * q < V) ? ld_row(p.lambda + (size_t)loc * V + lane + 32 * q) : 1024.0;
+      }
+    };
     auto b_from_row = [&](uint32_t loc, double *dst, double *row_dst) {
       double own[VPL];
-      fence_gpu();
-#pragma unroll
-      for (int q = 0; q < VPL; ++q) {
-        const int v = lane + 32 * q;
-        own[q] = (v < V) ? ld_row(p.lambda + (size_t)loc * V + v) : 1024.0;
-      }
+      load_row(loc, own);
 #pragma unroll
       for (int q = 0; q < VPL; ++q) {
         const int v = lane + 32 * q;
@@ -304,12 +302,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
           lam[q] = (v < V) ? s_row0[(i & 1) * V + v] : 1024.0;
         }
       } else if (it.loc != prev_loc) {
-        fence_gpu();
-#pragma unroll
-        for (int q = 0; q < VPL; ++q) {
-          const int v = lane + 32 * q;
-          lam[q] = (v < V) ? ld_row(p.lambda + (size_t)it.loc * V + v) : 1024.0;
-        }
+        load_row(it.loc, lam);
       }
       if (!prepared) {
 #pragma unroll
@@ -392,29 +385,15 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
             s1 = fma(en[k], bk.y, s1);
           }
           double enew[K];
-          gamma_one(bl, n, y, en, (double)y * fast_rcp(s0), (double)(2 - y) * fast_rcp(s1), enew);
+          gamma_one(bl, n, y, en, (double)y * fast_rcp1(s0), (double)(2 - y) * fast_rcp1(s1), enew);  // the E-step's q
 #pragma unroll
           for (int k = 0; k < K; ++k) p.E[(size_t)k * p.npad + n] = enew[k];
         }
       }
     };
-    bool tail = false;          // TS_OPT_SG: a last loop trip that only runs the gamma step
-    const double *bg = nullptr;  // the b the gamma step uses (the last executed E-step's)
     while (true) {
       const double *bx = x == 0 ? b_first : s_b + (x & 1) * V;
       const int par = (int)(rc & 1);
-      bool gamma_now = tail;
-      if (!tail) {
-#if TS_OPT_PRE
-      if constexpr (I > 0) {
-        if (x == 1 && i + 1 < n_items) {  // the loads complete behind this round; consumed at the next SNP
-          ncode = 0;
-#pragma unroll
-          for (int j = 0; j < I; ++j) ncode |= (unsigned)(valid[j] ? tsm::plink_code(nxt.col, nj[j]) : 1) << (2 * j);
-          have_ncode = true;
-        }
-      }
-#endif
       // ---- E-step over this thread's individuals: registers + broadcast shared-memory b --------
       double vv[V];
 #pragma unroll
@@ -431,13 +410,8 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
           s1 = fma(en[k], bk.y, s1);
         }
         // padding threads (no individual) have e = 0, s = 0: keep the reciprocal finite
-#if TS_OPT_N1
         q0 = w0 * fast_rcp1(ok ? s0 : 1.0);
         q1 = w1 * fast_rcp1(ok ? s1 : 1.0);
-#else
-        q0 = w0 * fast_rcp(ok ? s0 : 1.0);
-        q1 = w1 * fast_rcp(ok ? s1 : 1.0);
-#endif
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           vv[2 * k] = fma(en[k], q0, vv[2 * k]);
@@ -481,9 +455,8 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
         for (int ww = 0; ww < WS - 1; ++ww)
           if (ww < W) { hi += sh[ww]; lo += sl[ww]; }
         tsfx::normalize(hi, lo);  // the low word becomes [0, 2^44)
-        // row hand-off: these lanes of CTA 0 stored the previous SNP's row; by now that store has
-        // long been performed, so the fence that orders it before this arrival waits for nothing
-        if (x == 0 && blockIdx.x == 0) fence_gpu();
+        // row hand-off: these lanes of CTA 0 stored the rows of the SNPs before this one
+        if (x == 0 && blockIdx.x == 0 && (i % (RING / 2)) == 0 && i > 0) fence_gpu();
         if (p.xmode == XMODE_MCRED) {  // in-switch: one arrival per CTA on EVERY GPU's copy of the word
           mm_red_add(&p.pst_mc->acc[par][v][0], (unsigned long long)hi + (1ull << tsfx::MC_CNT_SHIFT));
           mm_red_add(&p.pst_mc->acc[par][V + v][0], ((unsigned long long)lo >> tsfx::MC_LO_DROP) + (1ull << tsfx::MC_CNT_SHIFT));
@@ -496,14 +469,11 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
       // The last round's totals only feed lambda[loc] (the gamma step uses the phi of THIS E-step),
       // so when this round is known to be the last one the gamma step runs now, in the shadow of
       // the grid barrier, and the control warp collects the totals afterwards.
-      if (x + 1 >= p.max_rounds && !(it.flags & ITEM_HOL)) { gamma_now = true; bg = bx; }
-      }  // !tail
-      if (gamma_now) {
+      if (x + 1 >= p.max_rounds && !(it.flags & ITEM_HOL)) {
         prepare_next();
-        if (!(it.flags & ITEM_HOL)) gamma_step(bg);
+        gamma_step(bx);
         gamma_done = true;
       }
-      if (tail) break;
       // ---- control warp: grid barrier + totals, lambda update, convergence, new b -------------
       if (warp == 0) {
         __syncwarp();  // the gamma step above has lane-dependent control flow
@@ -523,9 +493,13 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
               // count (ranks x CTAs) and the packed low word
               const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q];
               while (true) {
-                dh = ld_relaxed_sys(&st->acc[par][v][0]) - bh;
-                dl = ld_relaxed_sys(&st->acc[par][V + v][0]) - bl;
-                if ((dh >> tsfx::MC_CNT_SHIFT) == p.mc_arrivals && (dl >> tsfx::MC_CNT_SHIFT) == p.mc_arrivals) break;
+                bool complete = false;
+                for (int t = 0; t < POLL_BURST; ++t) {
+                  dh = ld_relaxed_sys(&st->acc[par][v][0]) - bh;
+                  dl = ld_relaxed_sys(&st->acc[par][V + v][0]) - bl;
+                  if ((dh >> tsfx::MC_CNT_SHIFT) == p.mc_arrivals && (dl >> tsfx::MC_CNT_SHIFT) == p.mc_arrivals) { complete = true; break; }
+                }
+                if (complete) break;
                 if (guard.expired(p.timeout_ns)) { abort = true; break; }
               }
               if (par) { ph1[q] = bh + dh; pl1[q] = bl + dl; } else { ph0[q] = bh + dh; pl0[q] = bl + dl; }
@@ -535,9 +509,13 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
             } else if (p.nranks == 1 || blockIdx.x == 0) {
               const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q];
               while (true) {
-                dh = ld_relaxed(&st->acc[par][v][0]) - bh;
-                dl = ld_relaxed(&st->acc[par][V + v][0]) - bl;
-                if ((dh >> FX_CNT_SHIFT) == G && (dl >> FX_CNT_SHIFT) == G) break;
+                bool complete = false;
+                for (int t = 0; t < POLL_BURST; ++t) {
+                  dh = ld_relaxed(&st->acc[par][v][0]) - bh;
+                  dl = ld_relaxed(&st->acc[par][V + v][0]) - bl;
+                  if ((dh >> FX_CNT_SHIFT) == G && (dl >> FX_CNT_SHIFT) == G) { complete = true; break; }
+                }
+                if (complete) break;
                 if (guard.expired(p.timeout_ns)) { abort = true; break; }
               }
               if (par) { ph1[q] = bh + dh; pl1[q] = bl + dl; } else { ph0[q] = bh + dh; pl0[q] = bl + dl; }
@@ -562,13 +540,15 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
                 for (int u = 0; u < 8; ++u)
                   if (r0 + u < p.nranks) pending |= 1u << u;
                 while (pending) {
+                  for (int t = 0; t < POLL_BURST && pending; ++t) {
 #pragma unroll
-                  for (int u = 0; u < 8; ++u)
-                    if (pending & (1u << u)) ld_pair_sys(&st->slot[r0 + u][par][v][0], wh[u], wl[u]);
+                    for (int u = 0; u < 8; ++u)
+                      if (pending & (1u << u)) ld_pair_sys(&st->slot[r0 + u][par][v][0], wh[u], wl[u]);
 #pragma unroll
-                  for (int u = 0; u < 8; ++u)
-                    if ((pending & (1u << u)) && (wh[u] & ~FX_MASK) == tag && (wl[u] & ~FX_MASK) == tag) pending &= ~(1u << u);
-                  if (guard.expired(p.timeout_ns)) { abort = true; break; }
+                    for (int u = 0; u < 8; ++u)
+                      if ((pending & (1u << u)) && (wh[u] & ~FX_MASK) == tag && (wl[u] & ~FX_MASK) == tag) pending &= ~(1u << u);
+                  }
+                  if (pending && guard.expired(p.timeout_ns)) { abort = true; break; }
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
@@ -623,10 +603,15 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
           chg = warp_sum(chg);
           done = chg / (double)V < p.thresh;
         }
-        if (done && blockIdx.x == 0) {
+        if (done) {  // the finished row: into this CTA's ring, and (CTA 0) to global memory
+          const int slot = (int)(i % RING);
+          if (lane < RING && (lane == slot || s_ring_loc[lane] == it.loc)) s_ring_loc[lane] = lane == slot ? it.loc : 0xffffffffu;
 #pragma unroll
           for (int q = 0; q < VPL; ++q)
-            if (lane + 32 * q < V) st_row(p.lambda + (size_t)it.loc * V + lane + 32 * q, own[q]);
+            if (lane + 32 * q < V) {
+              s_ring[slot * V + lane + 32 * q] = own[q];
+              if (blockIdx.x == 0) st_row(p.lambda + (size_t)it.loc * V + lane + 32 * q, own[q]);
+            }
         }
         if (lane == 0) {
           if (abort) { st->fault = 1; *s_flag = 2; }
@@ -641,25 +626,15 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
       ++rc;
       const int flag = *s_flag;
       if (flag & 2) return;
-#if TS_OPT_SG
-      if (flag & 1) {
-        if (gamma_done) break;
-        tail = true;  // early-converged SNPs and hol items: one more trip for the gamma step / the helper
-        bg = x == 1 ? b_first : s_b + ((x - 1) & 1) * V;
-      }
-#else
       if (flag & 1) break;
-#endif
     }
 
     // early-converged SNPs take the gamma step here; the usual case (all rounds run) took it
     // inside the last round, in the shadow of that round's grid barrier
-#if !TS_OPT_SG
     if (!gamma_done) {
       prepare_next();
       if (!(it.flags & ITEM_HOL)) gamma_step(x == 1 ? b_first : s_b + ((x - 1) & 1) * V);
     }
-#endif
     TS_TRACE(100);
     __syncthreads();  // s_b is rewritten for the next SNP
     TS_TRACE(101);

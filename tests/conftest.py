@@ -14,6 +14,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run by the driver with -m gpu)")
 
 
+def mask_text(t):
+    """Mask what legitimately differs between two runs of the same command: seconds in progress
+    lines, and the date + pid prefix of infer.log lines (log.cc: "[%b %e %T] [pid] [ERR] ")."""
+    import re
+    t = re.sub(r"took \d+ secs", "took # secs", t)
+    t = re.sub(r"@ \d+ secs", "@ # secs", t)
+    t = re.sub(r"(?m)^\[[A-Z][a-z]{2} [ \d]\d \d\d:\d\d:\d\d\] \[\d+\]", "[DATE] [PID]", t)
+    return t
+
+
 def load_fixture_rows():
     """The reference's bundled data set (data/test.bed, N=200 x L=10000): PLINK-packed rows [10000, 50].
     Stored as a compressed array (tools/make_golden.py) rather than as a copy of the .bed file."""

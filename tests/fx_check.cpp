@@ -113,6 +113,38 @@ int main() {
     REQUIRE(fabsl((long double)good - ref) <= fabsl(ref) * 1.2e-16L);
     REQUIRE(fabsl((long double)bad - ref) > fabsl(ref) * 1e-13L);
   }
+  // in-switch (NVLS) packing, XMODE_MCRED: 8 x 148 arrivals per word, 11 count bits, low word sent as lo >> 2
+  {
+    const int ranks = 8, ctas = 148, warps = 8, sh = tsfx::shift_for(1000000);
+    const tsfx::Unscale u = tsfx::unscale(std::ldexp(1.0, -sh));
+    unsigned long long acc_hi = 0xfff0000000000123ull, acc_lo = 0x8000000000000000ull;  // arbitrary history, wraps
+    const unsigned long long prev_hi = acc_hi, prev_lo = acc_lo;
+    i128 exact = 0;
+    for (int c = 0; c < ranks * ctas; ++c) {
+      long long hi = 0, lo = 0;
+      for (int w = 0; w < warps; ++w) {
+        long long h, l;
+        tsfx::split(1000.0 + 0.999 * U(g) + 0.0004, h, l);
+        exact += ((i128)h << 44) + l;
+        hi += h;
+        lo += l;
+      }
+      tsfx::normalize(hi, lo);
+      acc_hi += (unsigned long long)hi + (1ull << tsfx::MC_CNT_SHIFT);
+      acc_lo += ((unsigned long long)lo >> tsfx::MC_LO_DROP) + (1ull << tsfx::MC_CNT_SHIFT);
+    }
+    unsigned long long dh = acc_hi - prev_hi, dl = acc_lo - prev_lo;
+    REQUIRE((dh >> tsfx::MC_CNT_SHIFT) == (unsigned long long)(ranks * ctas) && (dl >> tsfx::MC_CNT_SHIFT) == (unsigned long long)(ranks * ctas));
+    dh &= tsfx::MC_MASK;
+    dl &= tsfx::MC_MASK;
+    tsfx::mc_unpack(dh, dl);
+    REQUIRE(dh < (1ull << 52) && dl < (1ull << 44));
+    const double got = tsfx::to_double(dh, dl, u);
+    const long double ref = ((long double)(long long)(exact >> 44) + std::ldexp((long double)(long long)(exact & (((i128)1 << 44) - 1)), -44)) *
+                            std::ldexp(1.0L, -sh);
+    // at most 3 units of 2^-44 dropped per CTA
+    REQUIRE(fabsl((long double)got - ref) <= std::ldexp((long double)(4 * ranks * ctas), -44 - sh) + fabsl(ref) * 1.2e-16L);
+  }
   printf("ok\n");
   return 0;
 }

@@ -55,8 +55,8 @@ extern "C" int km_train(uint32_t n, uint32_t l, uint32_t k, const uint8_t *y /* 
             s0 = std::fma(E[(size_t)i * k + kk], b[2 * kk], s0);
             s1 = std::fma(E[(size_t)i * k + kk], b[2 * kk + 1], s1);
           }
-          q0[i] = wt0 * tsp::fast_rcp(s0);
-          q1[i] = wt1 * tsp::fast_rcp(s1);
+          q0[i] = wt0 * tsp::fast_rcp1(s0);  // one Newton step, as in the kernel's E-step
+          q1[i] = wt1 * tsp::fast_rcp1(s1);
           for (uint32_t kk = 0; kk < k; ++kk) {
             vv[2 * kk] = std::fma(E[(size_t)i * k + kk], q0[i], vv[2 * kk]);
             vv[2 * kk + 1] = std::fma(E[(size_t)i * k + kk], q1[i], vv[2 * kk + 1]);

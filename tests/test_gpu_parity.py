@@ -648,3 +648,59 @@ def test_two_devices_match_one():
     assert rel_err(sh[0].get_lambda(), o.lam) < TIGHT
     assert res[0][1] + res[1][1] == c1 == cnt_o
     np.testing.assert_allclose(res[0][2] + res[1][2], per_o, rtol=1e-10, atol=1e-12)
+
+
+def test_cli_side_outputs_match_reference(tmp_path):
+    """f4 of SURVEY 8(f): what downstream scripts read besides theta/beta.  The CLI's stdout progress
+    lines, param.txt and infer.log of data/run.sh line 1, gammasave.txt (-idfile labels, snp.cc:256-276,
+    snpsamplinge.cc:839-861) and beta.txt under -locations-file (snpsamplinge.cc:385-413, :781-798)
+    against the reference binary's (tests/golden/fixture_text.json, tools/make_golden.py), byte for
+    byte after masking seconds, dates and pids.  Numbers inside gammasave/beta are compared at print
+    precision."""
+    import json
+    import os
+    import subprocess
+    from conftest import GOLDEN, ROOT, load_fixture_rows, mask_text
+    from terastructure_b200 import plink
+    gold = json.load(open(os.path.join(GOLDEN, "fixture_text.json")))
+    exe = os.path.join(ROOT, "terastructure_b200", "bin", "terastructure")
+    plink.write_bed(str(tmp_path / "test"), load_fixture_rows(), 200)
+    r = subprocess.run([exe, "-file", "test.bed", "-n", "200", "-l", "10000", "-k", "3", "-stochastic", "-nthreads", "1",
+                        "-rfreq", "1000", "-seed", "1234", "-label", "test"], cwd=tmp_path, capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = tmp_path / "n200-k3-l10000-test-seed1234"
+    assert mask_text(r.stdout.decode()) == gold["train_stdout"]
+    assert open(d / "param.txt").read() == gold["train_param"]
+    assert mask_text(open(d / "infer.log").read()) == gold["train_infer_log"]
+
+    (tmp_path / "ids.txt").write_text("".join("ind%03d\n" % i for i in range(200)))
+    (tmp_path / "locs_tab.txt").write_text("".join("%d\trs%d A G\n" % (x, x) for x in (5, 17, 4512, 9999, 17, 300)))
+    (tmp_path / "locs_bare.txt").write_text("".join("%d\n" % x for x in (5, 17, 4512, 9999, 17)))
+
+    def numeric_rows(text, skip):
+        return [[float(v) for v in line.split("\t")[skip:] if v.strip()] for line in text.splitlines()]
+
+    r = subprocess.run([exe, "-file", "../test.bed", "-n", "200", "-l", "10000", "-k", "3", "-stochastic", "-nthreads", "1",
+                        "-compute-beta", "-idfile", "../ids.txt", "-label", "idrun"], cwd=d, capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    b = d / "n200-k3-l10000-idrun"
+    assert mask_text(r.stdout.decode()) == gold["idrun_stdout"]
+    assert open(b / "param.txt").read() == gold["idrun_param"]
+    assert mask_text(open(b / "infer.log").read()) == gold["idrun_infer_log"]
+    ours, ref = open(b / "gammasave.txt").read(), gold["idrun_gammasave"]
+    assert [l.split("\t")[:2] for l in ours.splitlines()] == [l.split("\t")[:2] for l in ref.splitlines()]   # index, label
+    assert [l.split("\t")[-1] for l in ours.splitlines()] == [l.split("\t")[-1] for l in ref.splitlines()]   # argmax
+    # gamma.txt holds 8 decimals of the GPU run's gamma (within 1e-6 relative of the reference's): same here
+    np.testing.assert_allclose(np.array(numeric_rows(ours, 2))[:, :3], np.array(numeric_rows(ref, 2))[:, :3], rtol=1e-6, atol=2e-8)
+
+    for name in ("tab", "bare"):
+        r = subprocess.run([exe, "-file", "../test.bed", "-n", "200", "-l", "10000", "-k", "3", "-stochastic", "-nthreads", "1",
+                            "-compute-beta", "-locations-file", f"../locs_{name}.txt", "-label", f"loc{name}"],
+                           cwd=d, capture_output=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        b = d / f"n200-k3-l10000-loc{name}"
+        assert mask_text(open(b / "infer.log").read()) == gold[f"loc{name}_infer_log"]
+        assert mask_text(r.stdout.decode()) == gold[f"loc{name}_stdout"]
+        ours, ref = open(b / "beta.txt").read(), gold[f"loc{name}_beta"]
+        assert [l.split("\t")[0] for l in ours.splitlines()] == [l.split("\t")[0] for l in ref.splitlines()]
+        np.testing.assert_allclose(np.array(numeric_rows(ours, 1)), np.array(numeric_rows(ref, 1)), rtol=1e-6, atol=2e-8)

@@ -19,14 +19,13 @@ rng = ts.Rng(1234)
 vl, vo, vi = rng.sample_validation(n, l, None)
 e.set_validation(vl, vo, vi)
 e.set_gamma(rng.init_gamma(n, k)[rank * per:(rank + 1) * per])
-h = [None] * world
-dist.all_gather_object(h, e.comm_export())
-e.comm_connect(h)
+from terastructure_b200 import dist as tsdist
+xinfo = tsdist.connect(e)
 e.steps(rng.sample_locs(l, 200)); e.sync(); dist.barrier()
 e.timer_start(); e.steps(rng.sample_locs(l, 64)); ms = e.timer_stop()
 if rank == 0:
-    sys.stdout = open("gpurun_out/trace_mp_%d.txt" % world, "w")
-    print("%d GPUs: %.1f us per SNP" % (world, 1e3 * ms / 64))
+    sys.stdout = open("gpurun_out/trace_mp_%d_%s.txt" % (world, os.environ.get("TSGPU_XCHG", "default")), "w")
+    print("%d GPUs: %.1f us per SNP; exchange: %s" % (world, 1e3 * ms / 64, xinfo))
     t = e.debug_trace().astype(np.float64)
     it = t[8:60]
     def d(a, b): return np.mean(it[:, b] - it[:, a])
