@@ -174,17 +174,18 @@ int ts_sync(ts_engine *e);
 int ts_comm_export(ts_engine *e, void *handle_out);
 int ts_comm_connect(ts_engine *e, const void *all_handles /* nranks x 64 bytes, rank order */);
 int ts_comm_connect_local(ts_engine **engines, int n);
-/* Symmetric-memory exchange, with NVLS (NVSwitch multicast) when available.  The caller owns one
+/* Symmetric-memory exchange, optionally through NVLS (NVSwitch multicast).  The caller owns one
  * buffer of ts_comm_state_bytes() bytes per rank, each mapped on this engine's device:
  * rank_ptrs[nranks] (rank order, own rank included) and, optionally, a multicast pointer that
  * aliases the same offsets of ALL ranks' buffers (e.g. torch.distributed._symmetric_memory:
  * empty() + rendezvous() give buffer_ptrs and multicast_ptr).  The engine's exchange state moves into
- * its own buffer; with a multicast pointer the per-round exchange becomes an in-switch reduction
- * (every CTA of every rank adds its words with multimem.red; TSGPU_XCHG=mcslot|slots select the
- * other schemes for measurements).  Call it on every rank, then synchronise the ranks (a host
- * barrier) before the first ts_steps.  total_ctas = sum of the ranks' CTA counts (ts_get_plan), or 0
- * when all shards have this engine's geometry.  ts_comm_connect_local does all of this by itself for
- * the engines of one process. */
+ * its own buffer.  The scheme is chosen by TSGPU_XCHG in the environment: unset or "slots" = peer
+ * stores as with ts_comm_connect (the fastest measured, profiles/r2_summary.md); "mcslot" = CTA 0
+ * publishes the GPU totals with ONE multicast store (multimem.st); "mcred" = in-switch reduction,
+ * every CTA of every rank adds its words with multimem.red.  Call it on every rank, then
+ * synchronise the ranks (a host barrier) before the first ts_steps.  total_ctas = sum of the ranks'
+ * CTA counts (ts_get_plan), or 0 when all shards have this engine's geometry.  With TSGPU_XCHG=mcslot
+ * or mcred, ts_comm_connect_local does all of this by itself for the engines of one process. */
 uint64_t ts_comm_state_bytes(void);
 /* Exchange scheme in use: 0 peer stores into slots, 1 NVLS multicast store into slots, 2 NVLS
  * in-switch reduction (multimem.red from every CTA). */
@@ -194,14 +195,21 @@ int ts_comm_attach_symmetric(ts_engine *e, const void *const *rank_ptrs, void *m
 
 /* Launch geometry the engine uses for a shard of n_local individuals on a device with num_sms SMs
  * (pure host arithmetic, no device needed): individuals per thread held in registers by the
- * persistent kernel (0 = streaming variant for shards beyond the register-resident capacity),
- * CTAs and threads per CTA.  The reference's counterpart is the static split of individuals over
+ * persistent kernel, CTAs and threads per CTA.  The reference's counterpart is the static split of individuals over
  * `-nthreads` workers (split_all_indivs, snpsamplinge.cc:298-318). */
 int ts_plan_shard(uint64_t n_local, int k, int num_sms, int *ind_per_thread, int *grid, int *block);
 /* The geometry this engine runs with.  It differs from ts_plan_shard's only under the test knob
  * TSGPU_IPT=<i> (environment, read by ts_create), which pins the individuals per thread (0 = the
- * streaming variant) so that parity tests reach every kernel instantiation at oracle-sized inputs. */
+ * tiered kernel, see ts_get_tiers) so that parity tests reach every kernel instantiation at oracle-sized inputs. */
 int ts_get_plan(const ts_engine *e, int *ind_per_thread, int *grid, int *block);
+/* Shards beyond the register-resident capacity (148 x threads x individuals per thread) keep further
+ * individuals in the CTAs' shared memory and stream the rest from L2/HBM every round.  ts_plan_tiers:
+ * individuals per thread in shared memory and number of streamed individuals the engine would choose
+ * (0, 0 for a register-resident shard).  ts_get_tiers: what this engine runs with; smem_per_thread = -1
+ * means the register-only kernel.  Test knobs read by ts_create: TSGPU_IPT=0 forces the tiered kernel,
+ * TSGPU_TIER_J / TSGPU_TIER_GRID / TSGPU_TIER_BLOCK shape it. */
+int ts_plan_tiers(uint64_t n_local, int k, int num_sms, int *smem_per_thread, uint64_t *n_streamed);
+int ts_get_tiers(const ts_engine *e, int *smem_per_thread, uint64_t *n_streamed);
 
 /* ---- profiling hooks ------------------------------------------------------------------- */
 /* Kernels launched by this engine since creation (for bench.py's gpu_launches). */

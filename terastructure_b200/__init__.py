@@ -8,5 +8,5 @@ Only what the path needs lives here:
   plink.py         .bed/.bim/.fam reader that keeps genotypes 2-bit packed
   synth.py         PSD/Balding-Nichols synthetic genotype generator
 """
-from .capi import Engine, Rng, TsError, lib, plan_shard, LIB_PATH  # noqa: F401
+from .capi import Engine, Rng, TsError, lib, plan_shard, plan_tiers, LIB_PATH  # noqa: F401
 from .snpsamplinge import Env, SNPSamplingE  # noqa: F401

@@ -65,6 +65,8 @@ EXPORTS = {
     "ts_comm_attach_symmetric": (_i, [_vp, C.POINTER(_vp), _vp, _u64, _u32]),
     "ts_plan_shard": (_i, [_u64, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "ts_get_plan": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "ts_plan_tiers": (_i, [_u64, _i, _i, C.POINTER(_i), C.POINTER(_u64)]),
+    "ts_get_tiers": (_i, [_vp, C.POINTER(_i), C.POINTER(_u64)]),
     "ts_launch_count": (_u64, [_vp]),
     "ts_timer_start": (_i, [_vp]),
     "ts_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
@@ -305,6 +307,13 @@ class Engine:
         return ipt.value, grid.value, block.value
 
     @property
+    def tiers(self):
+        """(individuals per thread in shared memory, streamed individuals); (-1, 0) = register-only kernel."""
+        j, ns = C.c_int(), _u64()
+        check(lib().ts_get_tiers(self._h, C.byref(j), C.byref(ns)))
+        return j.value, ns.value
+
+    @property
     def launch_count(self):
         return lib().ts_launch_count(self._h)
 
@@ -334,9 +343,17 @@ def connect_local(engines):
     check(lib().ts_comm_connect_local(arr, len(engines)))
 
 
+def plan_tiers(n_local, k, num_sms=148):
+    """(individuals per thread in shared memory, individuals streamed from L2/HBM every round) the engine
+    chooses for a shard of `n_local` individuals; (0, 0) for a register-resident shard."""
+    j, ns = C.c_int(), _u64()
+    check(lib().ts_plan_tiers(n_local, k, num_sms, C.byref(j), C.byref(ns)))
+    return j.value, ns.value
+
+
 def plan_shard(n_local, k, num_sms=148):
     """(individuals per thread, CTAs, threads per CTA) the engine uses for a shard of `n_local`
-    individuals; individuals per thread 0 = streaming variant.  Host arithmetic only."""
+    individuals (register tier; plan_tiers gives the shared-memory and streaming tiers).  Host arithmetic only."""
     ipt, grid, block = C.c_int(), C.c_int(), C.c_int()
     check(lib().ts_plan_shard(n_local, k, num_sms, C.byref(ipt), C.byref(grid), C.byref(block)))
     return ipt.value, grid.value, block.value

@@ -97,6 +97,7 @@ struct Params {
   PState *pst_mc;                  // NVLS multicast alias of the symmetric PState (same offsets on all ranks), or null
   int xmode;                       // XMODE_*: how the ranks' totals of a round are exchanged
   unsigned long long mc_arrivals;  // XMODE_MCRED: CTAs per GPU x ranks = arrivals per word and round
+  uint32_t tier_j;          // TIER kernels: individuals per thread kept in shared memory
   double fx_scale, fx_inv;  // 2^sh and 2^-sh of the fixed-point statistics
   int xflush;               // fence.sys after the peer stores (TSGPU_XFLUSH, default off)
   unsigned long long timeout_ns;  // wall-clock limit of one grid/peer wait (TSGPU_TIMEOUT_S, default 60 s)
@@ -113,7 +114,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Persistent-kernel launcher, instantiated per K range in ts_persist_inst.cu (one translation unit
 // per range so that the build parallelises).  Returns cudaErrorInvalidValue for a (K, I) pair that
 // is not instantiated.
-cudaError_t ts_launch_persist(int K, int I, const Params &prm, uint32_t n_items, int grid, int block,
+cudaError_t ts_launch_persist(int K, int I, bool tier, const Params &prm, uint32_t n_items, int grid, int block,
                               cudaStream_t stream);
 int ts_persist_imax(int K);
+int ts_persist_itier(int K);
 int ts_persist_tmax(int K, int I);
+int ts_persist_tier_threads(void);
+size_t ts_persist_smem_base(int K, int threads);   // shared memory of a kernel compiled for `threads`, without the E tier
+size_t ts_persist_tier_slot_bytes(int K);          // shared memory per individual-per-thread of the E tier

@@ -10,12 +10,14 @@
 #include <sys/types.h>
 #include <unistd.h>
 
+#include <array>
 #include <cerrno>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <ctime>
 #include <fstream>
@@ -150,20 +152,40 @@ struct SNP {
     return nl;
   }
 
-  void count_codes() {  // "missing snps", "0s/1s/2s snps" lines of param.txt (snp.cc:243-247)
-    uint64_t lut[256][4];
-    for (int b = 0; b < 256; ++b) {
-      for (int c = 0; c < 4; ++c) lut[b][c] = 0;
-      for (int j = 0; j < 4; ++j) lut[b][(b >> (2 * j)) & 3]++;
-    }
-    uint64_t c[4] = {0, 0, 0, 0};
+  // "missing snps", "0s/1s/2s snps" lines of param.txt (snp.cc:243-247): one pass over the packed rows,
+  // 32 genotypes per 64-bit word (three popcounts), rows split over host threads -- at 250 GB the
+  // reference's per-genotype loop would take longer than the inference.
+  void count_codes() {
+    const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::array<uint64_t, 4>> part(nt, std::array<uint64_t, 4>{0, 0, 0, 0});
     const size_t full = env.n / 4, tail = env.n % 4;
-    for (uint32_t loc = 0; loc < env.l; ++loc) {
-      const uint8_t *r = rows + (size_t)loc * bps;
-      for (size_t i = 0; i < full; ++i)
-        for (int k = 0; k < 4; ++k) c[k] += lut[r[i]][k];
-      for (size_t j = 0; j < tail; ++j) c[(r[full] >> (2 * j)) & 3]++;
-    }
+    auto work = [&](unsigned t) {
+      const uint64_t M = 0x5555555555555555ull;
+      uint64_t c1 = 0, c2 = 0, c3 = 0, tot = 0, cz[4] = {0, 0, 0, 0};
+      for (uint32_t loc = t; loc < env.l; loc += nt) {
+        const uint8_t *r = rows + (size_t)loc * bps;
+        size_t i = 0;
+        for (; i + 8 <= full; i += 8) {
+          uint64_t x;
+          memcpy(&x, r + i, 8);
+          const uint64_t lo = x & M, hi = (x >> 1) & M;
+          c3 += __builtin_popcountll(lo & hi);
+          c1 += __builtin_popcountll(lo & ~hi);
+          c2 += __builtin_popcountll(hi & ~lo);
+          tot += 32;
+        }
+        for (; i < full; ++i)
+          for (int j = 0; j < 4; ++j) cz[(r[i] >> (2 * j)) & 3]++;
+        for (size_t j = 0; j < tail; ++j) cz[(r[full] >> (2 * j)) & 3]++;
+      }
+      part[t] = {cz[0] + (tot - c1 - c2 - c3), cz[1] + c1, cz[2] + c2, cz[3] + c3};
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+    for (auto &x : th) x.join();
+    uint64_t c[4] = {0, 0, 0, 0};
+    for (auto &pt : part)
+      for (int k = 0; k < 4; ++k) c[k] += pt[k];
     env.plog("missing snps", (uint32_t)c[1]);
     env.plog("0s snps", c[3]);  // the reference counts y=2 under "0s" (snp.cc:207-209)
     env.plog("1s snps", c[2]);
@@ -378,9 +400,11 @@ class SNPSamplingE {
       _local.push_back(cfg.n_local);
     }
     // read_bed's payload loop (snp.cc:186-229): ONE pass over the (memory-mapped) rows, every GPU takes its bytes
-    const time_t t0 = time(0);
+    const auto t0 = std::chrono::steady_clock::now();
     TSD_CHECK(ts_load_bed_fanout(_eng.data(), ng, 0, _l, _snp.rows, _snp.bps));
-    fprintf(stderr, "+ genotypes resident on %d GPU(s) after %d secs\n", ng, (int)(time(0) - t0));
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "+ genotypes resident on %d GPU(s): %.3f GB in %.2f s (%.2f GB/s)\n", ng, 1e-9 * (double)_l * _snp.bps, secs,
+            1e-9 * (double)_l * _snp.bps / std::max(secs, 1e-9));
     for (int r = 0; r < ng; ++r) TSD_CHECK(ts_set_validation(_eng[r], _nval, _val_loc, _val_off, _val_indiv));
     if (ng > 1) TSD_CHECK(ts_comm_connect_local(_eng.data(), ng));
   }

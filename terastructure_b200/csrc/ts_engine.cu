@@ -452,6 +452,8 @@ struct ts_engine {
   SymmGroup *symm = nullptr; // owned by rank 0's engine of a ts_comm_connect_local group
   bool staged = false;   // TSGPU_PATH=staged: one launch per round (debug cross-check path)
   int grid_persist = 1, block_persist = 32, ind_per_thread = 1;
+  bool tier = false;      // TIER kernel: registers + shared memory + streaming (ts_persist.cuh)
+  uint64_t n_stream = 0;  // individuals of this shard that stream from L2/HBM every round
   std::vector<void *> ipc_opened;
   // validation set (host copies)
   std::vector<uint32_t> val_loc;         // ascending
@@ -542,7 +544,7 @@ static void launch_heldout(ts_engine *e, unsigned n_items) {
 }
 
 static cudaError_t launch_persist(ts_engine *e, uint32_t n_items) {
-  return ts_launch_persist(e->K, e->ind_per_thread, e->prm, n_items, e->grid_persist, e->block_persist, e->stream);
+  return ts_launch_persist(e->K, e->ind_per_thread, e->tier, e->prm, n_items, e->grid_persist, e->block_persist, e->stream);
 }
 
 // Move the engine's exchange state into rank_ptrs[rank] (one buffer per rank, all reachable from this
@@ -561,10 +563,12 @@ static int attach_symmetric(ts_engine *e, void *const *rank_ptrs, void *mc, unsi
     e->prm.pst_peer[r] = &((Xchg *)rank_ptrs[r])->ps;
   }
   e->mc_arrivals = total_ctas;
-  const char *xm = getenv("TSGPU_XCHG");  // slots | mcslot | mcred (measurements: profiles/r2_summary.md)
-  int mode = mc ? XMODE_MCRED : XMODE_SLOTS;
-  if (xm && !strcmp(xm, "slots")) mode = XMODE_SLOTS;
-  else if (xm && !strcmp(xm, "mcslot") && mc) mode = XMODE_MCSLOT;
+  // TSGPU_XCHG = slots | mcslot | mcred.  Measured on 2 B200s (profiles/r2_summary.md): peer stores 59.5-59.8 us
+  // per SVI iteration, one multicast store 60.5, in-switch multimem.red from every CTA 64.3 (148 x ranks
+  // atomics per word and GPU): the default stays the peer-store exchange, NVLS is opt-in.
+  const char *xm = getenv("TSGPU_XCHG");
+  int mode = XMODE_SLOTS;
+  if (xm && !strcmp(xm, "mcslot") && mc) mode = XMODE_MCSLOT;
   else if (xm && !strcmp(xm, "mcred") && mc) mode = XMODE_MCRED;
   if (mode == XMODE_MCRED && total_ctas >= (1ull << (64 - tsfx::MC_CNT_SHIFT))) mode = XMODE_MCSLOT;  // arrival counter too narrow
   e->xmode = mode;
@@ -606,15 +610,26 @@ void ts_config_defaults(ts_config *cfg, uint64_t n, uint64_t l, uint32_t k) {
 }
 
 // Launch geometry of the persistent kernel for a shard of n individuals.
-// I individuals per thread live in registers; among the I that fit, take the one with the fewest
-// warps on the busiest of the SM's four schedulers (the warp-level reduction and the CTA sum are
-// issue-bound per scheduler), not going below two; ties go to the smaller I (shorter dependent
-// FP64 chains, fewer registers).  Shards beyond the register-resident capacity run the streaming
-// variant (I = 0: E read from L2 every round).
-// B200, K = 10, us per SVI iteration: 60K individuals I=1/13 warps 30.9, I=2/7 warps 28.3;
-// 80K I=2/9 warps 30.9, I=3/6 warps 28.9; 100K I=2/11 warps 31.2, I=3/8 warps 29.7, I=4/6 warps 32.5.
-// pin < 0: choose; pin == 0: force the streaming variant; pin >= 1: the first I >= pin that fits.
-static void plan_shard(uint64_t n, int K, int num_sms, int pin, int *ipt, int *grid_out, int *block_out) {
+// Register tier: I individuals per thread live in registers; among the I that fit, take the one with
+// the fewest warps on the busiest of the SM's four schedulers (the warp-level reduction and the CTA
+// sum are issue-bound per scheduler), not going below two; ties go to the smaller I (shorter
+// dependent FP64 chains, fewer registers).  B200, K = 10, us per SVI iteration: 60K individuals
+// I=1/13 warps 30.9, I=2/7 warps 28.3; 80K I=2/9 warps 30.9, I=3/6 warps 28.9; 100K I=2/11 warps 31.2,
+// I=3/8 warps 29.7, I=4/6 warps 32.5.
+// Shards beyond the register-resident capacity run the TIER kernel: itier(K) individuals per thread
+// in registers, J more in shared memory (as many as fit), the rest streamed from L2/HBM every round.
+struct ShardPlan {
+  int ipt = 1, grid = 1, block = 32;
+  bool tier = false;
+  int tier_j = 0;
+  uint64_t n_stream = 0;
+};
+constexpr size_t SMEM_OPTIN_B200 = 232448;  // 227 KB of dynamic shared memory per CTA (sm_100)
+// pin < 0: choose; pin == 0: force the TIER kernel; pin >= 1: the first register-only I >= pin that fits.
+// pin_j / pin_grid / pin_block (< 0 or 0: choose) shape the TIER kernel in tests.
+static ShardPlan plan_shard(uint64_t n, int K, int num_sms, int pin, int pin_j = -1, int pin_grid = 0, int pin_block = 0,
+                            size_t smem_limit = SMEM_OPTIN_B200) {
+  ShardPlan pl;
   int I = 0, best = 1 << 30;
   for (int c = std::max(pin, 1); pin != 0 && c <= ts_persist_imax(K); ++c) {
     if ((uint64_t)num_sms * ts_persist_tmax(K, c) * c < n) continue;
@@ -625,22 +640,45 @@ static void plan_shard(uint64_t n, int K, int num_sms, int pin, int *ipt, int *g
     const int score = std::max((warps + 3) / 4, 2);
     if (score < best) { best = score; I = c; }
   }
-  *ipt = I;
-  if (I == 0) {
-    *grid_out = num_sms;
-    *block_out = ts_persist_tmax(K, 0);
-    return;
+  if (I > 0) {
+    const uint64_t threads = (n + I - 1) / I;
+    pl.ipt = I;
+    pl.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(num_sms, (threads + 63) / 64));  // all SMs once there are 2 warps each
+    const uint64_t t = (threads + pl.grid - 1) / pl.grid;
+    pl.block = (int)std::min<uint64_t>(ts_persist_tmax(K, I), std::max<uint64_t>(32, (t + 31) / 32 * 32));
+    return pl;
   }
-  const uint64_t threads = (n + I - 1) / I;
-  *grid_out = (int)std::max<uint64_t>(1, std::min<uint64_t>(num_sms, (threads + 63) / 64));  // all SMs once there are 2 warps each
-  const uint64_t t = (threads + *grid_out - 1) / *grid_out;
-  *block_out = (int)std::min<uint64_t>(ts_persist_tmax(K, I), std::max<uint64_t>(32, (t + 31) / 32 * 32));
+  pl.tier = true;
+  pl.ipt = ts_persist_itier(K);
+  pl.block = pin_block > 0 ? std::min(pin_block, ts_persist_tier_threads()) / 32 * 32 : ts_persist_tier_threads();
+  pl.block = std::max(pl.block, 32);
+  pl.grid = pin_grid > 0 ? std::min(pin_grid, num_sms) : num_sms;
+  const uint64_t gt = (uint64_t)pl.grid * pl.block;
+  const uint64_t rest = n > (uint64_t)pl.ipt * gt ? n - (uint64_t)pl.ipt * gt : 0;
+  const size_t base = ts_persist_smem_base(K, ts_persist_tier_threads());
+  const int jmax = (int)std::min<size_t>(16, smem_limit > base ? (smem_limit - base) / ts_persist_tier_slot_bytes(K) : 0);
+  pl.tier_j = pin_j >= 0 ? std::min(pin_j, jmax) : (int)std::min<uint64_t>(jmax, (rest + gt - 1) / gt);
+  const uint64_t held = (uint64_t)(pl.ipt + pl.tier_j) * gt;
+  pl.n_stream = n > held ? n - held : 0;
+  return pl;
 }
 
 int ts_plan_shard(uint64_t n_local, int k, int num_sms, int *ind_per_thread, int *grid, int *block) {
   if (k < 1 || k > TS_MAX_K || num_sms < 1 || !ind_per_thread || !grid || !block)
     return set_err(TS_ERR_ARG, "ts_plan_shard: K=%d outside 1..%d, num_sms=%d or null output", k, TS_MAX_K, num_sms);
-  plan_shard(n_local, k, num_sms, -1, ind_per_thread, grid, block);
+  const ShardPlan pl = plan_shard(n_local, k, num_sms, -1);
+  *ind_per_thread = pl.ipt;
+  *grid = pl.grid;
+  *block = pl.block;
+  return TS_OK;
+}
+
+int ts_plan_tiers(uint64_t n_local, int k, int num_sms, int *smem_per_thread, uint64_t *n_streamed) {
+  if (k < 1 || k > TS_MAX_K || num_sms < 1 || !smem_per_thread || !n_streamed)
+    return set_err(TS_ERR_ARG, "ts_plan_tiers: K=%d outside 1..%d, num_sms=%d or null output", k, TS_MAX_K, num_sms);
+  const ShardPlan pl = plan_shard(n_local, k, num_sms, -1);
+  *smem_per_thread = pl.tier ? pl.tier_j : 0;
+  *n_streamed = pl.n_stream;
   return TS_OK;
 }
 
@@ -715,11 +753,21 @@ int ts_create(const ts_config *cfg, ts_engine **out) {
     // same number of individuals (I = ceil(n / (SMs * TMAX))).
     const char *path = getenv("TSGPU_PATH");
     e->staged = path && !strcmp(path, "staged");
-    // test/developer knob: pin the individuals per thread (0 = the streaming variant), so that the
-    // parity tests reach every instantiation at sizes the oracle finishes in seconds
-    const char *force = getenv("TSGPU_IPT");
-    plan_shard(cfg->n_local, e->K, e->num_sms, force ? std::max(0, atoi(force)) : -1, &e->ind_per_thread, &e->grid_persist,
-               &e->block_persist);
+    // test/developer knobs: TSGPU_IPT pins the individuals per thread in registers (0 = the TIER kernel);
+    // TSGPU_TIER_J / TSGPU_TIER_GRID / TSGPU_TIER_BLOCK shape the TIER kernel so that the parity tests
+    // reach its shared-memory and streaming tiers at sizes the oracle finishes in seconds
+    auto env_int = [](const char *name, int dflt) { const char *v = getenv(name); return v ? atoi(v) : dflt; };
+    int optin = 0;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+    const ShardPlan pl = plan_shard(cfg->n_local, e->K, e->num_sms, std::max(-1, env_int("TSGPU_IPT", -1)), env_int("TSGPU_TIER_J", -1),
+                                    env_int("TSGPU_TIER_GRID", 0), env_int("TSGPU_TIER_BLOCK", 0),
+                                    optin > 0 ? (size_t)optin : SMEM_OPTIN_B200);
+    e->ind_per_thread = pl.ipt;
+    e->grid_persist = pl.grid;
+    e->block_persist = pl.block;
+    e->tier = pl.tier;
+    e->prm.tier_j = (uint32_t)pl.tier_j;
+    e->n_stream = pl.n_stream;
     const char *tmo = getenv("TSGPU_TIMEOUT_S");
     e->prm.timeout_ns = (unsigned long long)(1e9 * (tmo ? std::max(0.001, atof(tmo)) : 60.0));
     const int sh = tsfx::shift_for(cfg->n_total);  // per-warp sums stay below 2^52 (mantissa-trick conversion)
@@ -1212,14 +1260,14 @@ int ts_comm_connect_local(ts_engine **engines, int n) {
       e->prm.pst_peer[j] = &engines[j]->xchg->ps;
     }
   }
-  // Distinct devices: move the exchange state into symmetric buffers with an NVLS multicast alias when
-  // the fabric offers one (TSGPU_XCHG=slots keeps the plain peer-store exchange).
+  // Opt-in (TSGPU_XCHG=mcslot|mcred, distinct devices): move the exchange state into symmetric buffers
+  // with an NVLS multicast alias when the fabric offers one.  Default: the peer-store exchange above.
   bool distinct = n > 1;
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < i; ++j)
       if (engines[i]->cfg.device == engines[j]->cfg.device) distinct = false;
   const char *xm = getenv("TSGPU_XCHG");
-  if (distinct && !(xm && !strcmp(xm, "slots")) && !engines[0]->symm) {
+  if (distinct && xm && (!strcmp(xm, "mcslot") || !strcmp(xm, "mcred")) && !engines[0]->symm) {
     std::vector<int> devs(n);
     for (int i = 0; i < n; ++i) devs[i] = engines[i]->cfg.device;
     std::string err;
@@ -1259,6 +1307,13 @@ int ts_get_plan(const ts_engine *e, int *ind_per_thread, int *grid, int *block) 
   *ind_per_thread = e->ind_per_thread;
   *grid = e->grid_persist;
   *block = e->block_persist;
+  return TS_OK;
+}
+
+int ts_get_tiers(const ts_engine *e, int *smem_per_thread, uint64_t *n_streamed) {
+  if (!e || !smem_per_thread || !n_streamed) return set_err(TS_ERR_ARG, "ts_get_tiers: null argument");
+  *smem_per_thread = e->tier ? (int)e->prm.tier_j : -1;
+  *n_streamed = e->n_stream;
   return TS_OK;
 }
 

@@ -28,6 +28,8 @@
 //
 // No host round trip, no kernel launch and no fence on the critical path of a round.
 #pragma once
+#include <type_traits>
+
 #include "ts_expsi.cuh"
 #include "ts_fixed.cuh"
 
@@ -159,29 +161,66 @@ struct SpinGuard {
 // the strong loads).  Price of the fence on CTA 0's path: ~950 cycles, once per RING / 2 SNPs.
 constexpr int RING = 8;
 
-// I >= 1: I individuals per thread live in registers; threads per CTA are capped so that the
-// register file holds them.  I == 0: streaming variant for shards beyond that capacity -- every
-// thread strides over the shard and reads E = exp(psi(gamma)) from global memory (L2) each round.
-__host__ __device__ constexpr int persist_imax(int K) { return K <= 20 ? 4 : 1; }
+// Where a shard's E = exp(psi(gamma)) rows live during a launch (all tiers read them every round):
+//   registers      I individuals per thread (k_persist<K, I, false>): shards up to 148 x T x I
+//   shared memory  TIER kernels (k_persist<K, I, true>): J more individuals per thread in the CTA's
+//                  shared memory (layout [j][k][thread]: conflict-free), J chosen at launch
+//   global memory  TIER kernels: what is left streams from L2/HBM every round
+// Individual n = m * (grid x T) + global thread id; m < I: registers, m < I + J: shared, else global.
+// Threads per CTA are capped so that the register file holds the register tier without spills.
+__host__ __device__ constexpr int persist_imax(int K) { return K <= 12 ? 4 : (K <= 20 ? 3 : 1); }
+__host__ __device__ constexpr int persist_itier(int K) { return K <= 12 ? 2 : 1; }  // register tier of the TIER kernels
+constexpr int TIER_THREADS = 256;
+constexpr int TIER_JMAX = 16;  // codes of the shared-memory tier travel as 2 bits each in one register
 __host__ __device__ constexpr int persist_tmax(int K, int I) {
-  if (I == 0) return K <= 12 ? 512 : (K <= 20 ? 384 : 256);  // streaming: E read from L2 every round
 #ifndef TS_I3_TMAX
 #define TS_I3_TMAX 256  // registers are allocated per 4 warps: 288 threads would cap at 168 registers like 384 do (spills)
 #endif
-  return K <= 12 ? (I == 1 ? 512 : (I == 2 ? 384 : (I == 3 ? TS_I3_TMAX : 256)))
-                 : (K <= 20 ? (I == 1 ? 384 : (I == 2 ? 256 : (I == 3 ? 224 : 192))) : 256);
+  return K <= 12 ? (I == 1 ? 512 : (I == 2 ? 384 : (I == 3 ? TS_I3_TMAX : 256))) : (K <= 20 && I == 1 ? 384 : 256);
 }
-__host__ __device__ constexpr size_t persist_smem_bytes(int K, int I) {
-  return sizeof(double) * ((12 + 2 * RING) * K) + sizeof(uint32_t) * RING + sizeof(long long) * (4 * K * (persist_tmax(K, I) / 32 + 1)) + 16;
+// shared memory without the E tier, for a kernel compiled for at most T threads per CTA (multiple of 16 bytes)
+__host__ __device__ constexpr size_t persist_smem_bytes(int K, int T) {
+  return (sizeof(double) * ((12 + 2 * RING) * K) + sizeof(long long) * (4 * K * (T / 32 + 1)) + 16 + sizeof(uint32_t) * RING + 15) / 16 * 16;
+}
+// bytes of shared-memory E tier per individual-per-thread slot
+__host__ __device__ constexpr size_t persist_tier_slot_bytes(int K) { return sizeof(double) * K * TIER_THREADS; }
+
+// s_t = sum_k E[k] b[k][t], t = 0, 1 (the softmax denominators of the E-step).  SPLIT = false: one
+// dependent FMA chain per t (register tier: three individuals per thread give the FP64 pipe enough
+// independent chains).  SPLIT = true: two half-length chains per t for the shared-memory and streaming
+// tiers, whose individuals pass one or two at a time (dependent DFMA latency on B200: ~23 cycles).
+template <int K, bool SPLIT>
+__device__ __forceinline__ void dot_b(const double (&en)[K], const double *b, double &s0, double &s1) {
+  if constexpr (!SPLIT || K < 4) {
+    s0 = 0.0;
+    s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double2 bk = *reinterpret_cast<const double2 *>(b + 2 * k);
+      s0 = fma(en[k], bk.x, s0);
+      s1 = fma(en[k], bk.y, s1);
+    }
+  } else {
+    double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double2 bk = *reinterpret_cast<const double2 *>(b + 2 * k);
+      if (k & 1) { c0 = fma(en[k], bk.x, c0); c1 = fma(en[k], bk.y, c1); }
+      else { a0 = fma(en[k], bk.x, a0); a1 = fma(en[k], bk.y, a1); }
+    }
+    s0 = a0 + c0;
+    s1 = a1 + c1;
+  }
 }
 
-
-template <int K, int I>
-__global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uint32_t n_items) {
+template <int K, int I, bool TIER>
+__global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k_persist(Params p, uint32_t n_items) {
+  static_assert(I >= 1, "the register tier holds at least one individual per thread");
   constexpr int V = 2 * K;
   constexpr int NW = 2 * V;           // fixed-point words per round: word = hl * V + v
   constexpr int VPL = (V + 31) / 32;  // statistics per lane of the control warp
-  constexpr int WS = persist_tmax(K, I) / 32 + 1;
+  constexpr int TM = TIER ? TIER_THREADS : persist_tmax(K, I);
+  constexpr int WS = TM / 32 + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *s_b = reinterpret_cast<double *>(smem_raw);                // [2][V]: b of round x >= 1 at [x&1]
   double *s_b0 = s_b + 2 * V;                                        // [2][V]: b of round 0 of SNP i at [i&1]
@@ -190,6 +229,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
   long long *s_fix = reinterpret_cast<long long *>(s_ring + RING * V);  // [NW][WS] per-warp fixed-point words
   int *s_flag = reinterpret_cast<int *>(s_fix + NW * WS);  // bit 0: round loop done, bit 1: abort
   uint32_t *s_ring_loc = reinterpret_cast<uint32_t *>(s_flag + 4);  // [RING]: locus of a ring slot, ~0 = empty
+  double *s_E = reinterpret_cast<double *>(smem_raw + persist_smem_bytes(K, TM));  // TIER: [J][K][blockDim.x]
 
   PState *st = p.pst;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
@@ -221,18 +261,28 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
   uint32_t prev_loc = 0xffffffffu;
   if (tid < RING) s_ring_loc[tid] = 0xffffffffu;
 
-  // this thread's individuals and their E = exp(psi(gamma)) rows, register-resident (I >= 1)
-  constexpr int IR = I > 0 ? I : 1;
+  // this thread's individuals and their E = exp(psi(gamma)) rows: register tier
+  constexpr int IR = I;
   uint32_t nj[IR];
   bool valid[IR];
   double e[IR][K];
-  if constexpr (I > 0) {
 #pragma unroll
-    for (int j = 0; j < I; ++j) {
-      nj[j] = gtid + (uint32_t)j * GT;
-      valid[j] = nj[j] < p.n_local;
+  for (int j = 0; j < I; ++j) {
+    nj[j] = gtid + (uint32_t)j * GT;
+    valid[j] = nj[j] < p.n_local;
 #pragma unroll
-      for (int k = 0; k < K; ++k) e[j][k] = valid[j] ? p.E[(size_t)k * p.npad + nj[j]] : 0.0;
+    for (int k = 0; k < K; ++k) e[j][k] = valid[j] ? p.E[(size_t)k * p.npad + nj[j]] : 0.0;
+  }
+  // shared-memory tier (J individuals per thread) and the first individual of the streaming tier
+  const int J = TIER ? (int)p.tier_j : 0;
+  const uint32_t T = blockDim.x;
+  const uint32_t stream_begin = (uint32_t)(I + J) * GT;
+  auto tier_n = [&](int j) { return (uint32_t)(I + j) * GT + gtid; };
+  if constexpr (TIER) {
+    for (int j = 0; j < J; ++j) {
+      const uint32_t n = tier_n(j);
+#pragma unroll
+      for (int k = 0; k < K; ++k) s_E[(size_t)(j * K + k) * T + tid] = n < p.n_local ? p.E[(size_t)k * p.npad + n] : 0.0;
     }
   }
   __syncthreads();
@@ -241,15 +291,18 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
     const WorkItem it = p.items[i];
     const unsigned char *col = it.col;
     int code[IR];
-    if constexpr (I > 0) {
-      {
 #pragma unroll
-        for (int j = 0; j < I; ++j) code[j] = valid[j] ? tsm::plink_code(col, nj[j]) : 1;
+    for (int j = 0; j < I; ++j) code[j] = valid[j] ? tsm::plink_code(col, nj[j]) : 1;
+    unsigned scode = 0;  // TIER: codes of the shared-memory tier, 2 bits per individual
+    if constexpr (TIER) {
+      for (int j = 0; j < J; ++j) {
+        const uint32_t n = tier_n(j);
+        scode |= (unsigned)(n < p.n_local ? tsm::plink_code(col, n) : 1) << (2 * j);
       }
     }
     if (i + 1 < n_items) {  // next SNP's genotype column and lambda row -> L2
       const WorkItem nx = p.items[i + 1];
-      if constexpr (I > 0) {
+      if constexpr (!TIER) {
 #pragma unroll
         for (int j = 0; j < I; ++j)
           if (valid[j] && (nj[j] & 511) == 0) prefetch_l2(nx.col + (nj[j] >> 2));  // one per 128-byte line
@@ -264,21 +317,22 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
     //
     // With a single permitted round the helper would run BEFORE this SNP's only barrier and before
     // the previous SNP's row exists anywhere (locus sequence A, B, A): no preparation then.
-    auto load_row = [&](uint32_t loc, double (&own)[VPL]) {  // whole warp: ring first, global memory otherwise
+    // whole warp: ring first, global memory otherwise (`fenced`: the caller ran the readers' fence already)
+    auto load_row = [&](uint32_t loc, double (&own)[VPL], bool fenced) {
       const unsigned hit = __ballot_sync(0xffffffffu, lane < RING && s_ring_loc[lane] == loc);
       if (hit) {
         const double *row = s_ring + (__ffs(hit) - 1) * V;
 #pragma unroll
         for (int q = 0; q < VPL; ++q) own[q] = (lane + 32 * q < V) ? row[lane + 32 * q] : 1024.0;
       } else {
-        fence_gpu();
+        if (!fenced) fence_gpu();
 #pragma unroll
         for (int q = 0; q < VPL; ++q) own[q] = (lane + 32 * q < V) ? ld_row(p.lambda + (size_t)loc * V + lane + 32 * q) : 1024.0;
       }
     };
     auto b_from_row = [&](uint32_t loc, double *dst, double *row_dst) {
       double own[VPL];
-      load_row(loc, own);
+      load_row(loc, own, true);
 #pragma unroll
       for (int q = 0; q < VPL; ++q) {
         const int v = lane + 32 * q;
@@ -295,6 +349,16 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
     const bool prepared = can_prepare && i > 0 && it.loc != prev_loc;
     double *b_first = s_b0 + (i & 1) * V;
     if (warp == 0) {
+      if (i > 0) {
+        // the previous SNP's finished row (still in `lam`) enters this CTA's ring here, not where it
+        // was formed: the helper warp may have been reading the ring until that SNP's last barrier
+        const int slot = (int)((i - 1) % RING);
+        if (lane < RING && (lane == slot || s_ring_loc[lane] == prev_loc)) s_ring_loc[lane] = lane == slot ? prev_loc : 0xffffffffu;
+#pragma unroll
+        for (int q = 0; q < VPL; ++q)
+          if (lane + 32 * q < V) s_ring[slot * V + lane + 32 * q] = lam[q];
+        __syncwarp();
+      }
       if (prepared) {  // the helper left the row next to b
 #pragma unroll
         for (int q = 0; q < VPL; ++q) {
@@ -302,7 +366,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
           lam[q] = (v < V) ? s_row0[(i & 1) * V + v] : 1024.0;
         }
       } else if (it.loc != prev_loc) {
-        load_row(it.loc, lam);
+        load_row(it.loc, lam, false);
       }
       if (!prepared) {
 #pragma unroll
@@ -319,7 +383,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
       }
       if (lane == 0) *s_flag = 0;
     }
-    // the helper's job for the NEXT SNP; called once per SNP by warp W-1, before its gamma step
+    // the helper's job for the NEXT SNP; called once per SNP by warp W-1
     auto prepare_next = [&]() {
       if (can_prepare && warp == W - 1 && i + 1 < n_items) {
         const uint32_t nloc = p.items[i + 1].loc;
@@ -334,7 +398,7 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
 
     uint32_t x = 0;
     double r0[IR], r1[IR];
-    bool gamma_done = false;
+    bool gamma_done = false, next_prepared = false;
     // ---- gamma natural-gradient step + E refresh (update_gamma/estimate_theta, cc:695-740) ----
     // phi of the LAST E-step: r0/r1 are still in registers, `bl` is the b that E-step used.
     auto gamma_one = [&](const double *bl, uint32_t n, int y, const double (&en)[K], double q0, double q1, double (&enew)[K]) {
@@ -356,38 +420,62 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
       }
       (void)y;
     };
+    // q of an individual outside the register tier, recomputed with the instruction sequence of the
+    // E-step (same bits as the phi that entered the round's statistics)
+    auto requantify = [&](const double *bl, int c, const double (&en)[K], double &q0, double &q1) {
+      const int y = tsm::code_to_y(c);
+      double s0, s1;
+      dot_b<K, true>(en, bl, s0, s1);
+      q0 = (double)y * fast_rcp1(s0);
+      q1 = (double)(2 - y) * fast_rcp1(s1);
+    };
     auto gamma_step = [&](const double *bl) {
-      if constexpr (I > 0) {
 #pragma unroll
-        for (int j = 0; j < I; ++j) {
-          if (code[j] == 1) continue;
-          gamma_one(bl, nj[j], tsm::code_to_y(code[j]), e[j], r0[j], r1[j], e[j]);
+      for (int j = 0; j < I; ++j) {
+        if (code[j] == 1) continue;
+        gamma_one(bl, nj[j], tsm::code_to_y(code[j]), e[j], r0[j], r1[j], e[j]);
+      }
+      if constexpr (TIER) {
+#pragma unroll 1
+        for (int j = 0; j < J; ++j) {  // shared-memory tier: E stays on chip, gamma streams through
+          const int c = (scode >> (2 * j)) & 3;
+          if (c == 1) continue;
+          double en[K], q0, q1;
+#pragma unroll
+          for (int k = 0; k < K; ++k) en[k] = s_E[(size_t)(j * K + k) * T + tid];
+          requantify(bl, c, en, q0, q1);
+          gamma_one(bl, tier_n(j), tsm::code_to_y(c), en, q0, q1, en);
+#pragma unroll
+          for (int k = 0; k < K; ++k) s_E[(size_t)(j * K + k) * T + tid] = en[k];
         }
-        if (i + 1 == n_items) {  // E leaves the registers only at the end of the launch
-#pragma unroll
-          for (int j = 0; j < I; ++j)
-            if (valid[j]) {
-#pragma unroll
-              for (int k = 0; k < K; ++k) p.E[(size_t)k * p.npad + nj[j]] = e[j][k];
-            }
-        }
-      } else {
-        for (uint32_t n = gtid; n < p.n_local; n += GT) {
+#pragma unroll 1
+        for (uint32_t n = stream_begin + gtid; n < p.n_local; n += GT) {  // streaming tier
           const int c = tsm::plink_code(col, n);
           if (c == 1) continue;
-          const int y = tsm::code_to_y(c);
-          double en[K], s0 = 0.0, s1 = 0.0;
+          double en[K], q0, q1;
 #pragma unroll
-          for (int k = 0; k < K; ++k) {
-            en[k] = p.E[(size_t)k * p.npad + n];
-            const double2 bk = *reinterpret_cast<const double2 *>(bl + 2 * k);
-            s0 = fma(en[k], bk.x, s0);
-            s1 = fma(en[k], bk.y, s1);
+          for (int k = 0; k < K; ++k) en[k] = p.E[(size_t)k * p.npad + n];
+          requantify(bl, c, en, q0, q1);
+          gamma_one(bl, n, tsm::code_to_y(c), en, q0, q1, en);
+#pragma unroll
+          for (int k = 0; k < K; ++k) p.E[(size_t)k * p.npad + n] = en[k];
+        }
+      }
+      if (i + 1 == n_items) {  // E leaves the chip only at the end of the launch
+#pragma unroll
+        for (int j = 0; j < I; ++j)
+          if (valid[j]) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) p.E[(size_t)k * p.npad + nj[j]] = e[j][k];
           }
-          double enew[K];
-          gamma_one(bl, n, y, en, (double)y * fast_rcp1(s0), (double)(2 - y) * fast_rcp1(s1), enew);  // the E-step's q
+        if constexpr (TIER) {
+          for (int j = 0; j < J; ++j) {
+            const uint32_t n = tier_n(j);
+            if (n < p.n_local) {
 #pragma unroll
-          for (int k = 0; k < K; ++k) p.E[(size_t)k * p.npad + n] = enew[k];
+              for (int k = 0; k < K; ++k) p.E[(size_t)k * p.npad + n] = s_E[(size_t)(j * K + k) * T + tid];
+            }
+          }
         }
       }
     };
@@ -398,17 +486,12 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
       double vv[V];
 #pragma unroll
       for (int v = 0; v < V; ++v) vv[v] = 0.0;
-      auto estep_one = [&](int c, bool ok, const double (&en)[K], double &q0, double &q1) {
+      auto estep_one = [&](auto split, int c, bool ok, const double (&en)[K], double &q0, double &q1) {
         // missing or held out (kv_ok, hh:389-408) -> weight 0; branch-free, the warp stays converged
         const int y = tsm::code_to_y(c);
         const double w0 = (c == 1) ? 0.0 : (double)y, w1 = (c == 1) ? 0.0 : (double)(2 - y);
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const double2 bk = *reinterpret_cast<const double2 *>(bx + 2 * k);
-          s0 = fma(en[k], bk.x, s0);
-          s1 = fma(en[k], bk.y, s1);
-        }
+        double s0, s1;
+        dot_b<K, decltype(split)::value>(en, bx, s0, s1);
         // padding threads (no individual) have e = 0, s = 0: keep the reciprocal finite
         q0 = w0 * fast_rcp1(ok ? s0 : 1.0);
         q1 = w1 * fast_rcp1(ok ? s1 : 1.0);
@@ -418,15 +501,22 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
           vv[2 * k + 1] = fma(en[k], q1, vv[2 * k + 1]);
         }
       };
-      if constexpr (I > 0) {
 #pragma unroll
-        for (int j = 0; j < I; ++j) estep_one(code[j], valid[j], e[j], r0[j], r1[j]);
-      } else {
-        for (uint32_t n = gtid; n < p.n_local; n += GT) {
+      for (int j = 0; j < I; ++j) estep_one(std::false_type{}, code[j], valid[j], e[j], r0[j], r1[j]);
+      if constexpr (TIER) {
+#pragma unroll(K <= 12 ? 2 : 1)
+        for (int j = 0; j < J; ++j) {  // shared-memory tier, two individuals in flight while registers allow
           double en[K], q0, q1;
 #pragma unroll
-          for (int k = 0; k < K; ++k) en[k] = p.E[(size_t)k * p.npad + n];
-          estep_one(tsm::plink_code(col, n), true, en, q0, q1);
+          for (int k = 0; k < K; ++k) en[k] = s_E[(size_t)(j * K + k) * T + tid];
+          estep_one(std::true_type{}, (scode >> (2 * j)) & 3, tier_n(j) < p.n_local, en, q0, q1);
+        }
+#pragma unroll(K <= 12 ? 2 : 1)
+        for (uint32_t n = stream_begin + gtid; n < p.n_local; n += GT) {  // streaming tier: E from L2/HBM
+          double en[K], q0, q1;
+#pragma unroll
+          for (int k = 0; k < K; ++k) en[k] = __ldcg(p.E + (size_t)k * p.npad + n);
+          estep_one(std::true_type{}, tsm::plink_code(col, n), true, en, q0, q1);
         }
         __syncwarp();  // lane-dependent trip count: reconverge before the shuffles
       }
@@ -455,8 +545,6 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
         for (int ww = 0; ww < WS - 1; ++ww)
           if (ww < W) { hi += sh[ww]; lo += sl[ww]; }
         tsfx::normalize(hi, lo);  // the low word becomes [0, 2^44)
-        // row hand-off: these lanes of CTA 0 stored the rows of the SNPs before this one
-        if (x == 0 && blockIdx.x == 0 && (i % (RING / 2)) == 0 && i > 0) fence_gpu();
         if (p.xmode == XMODE_MCRED) {  // in-switch: one arrival per CTA on EVERY GPU's copy of the word
           mm_red_add(&p.pst_mc->acc[par][v][0], (unsigned long long)hi + (1ull << tsfx::MC_CNT_SHIFT));
           mm_red_add(&p.pst_mc->acc[par][V + v][0], ((unsigned long long)lo >> tsfx::MC_LO_DROP) + (1ull << tsfx::MC_CNT_SHIFT));
@@ -466,11 +554,21 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
         }
       }
       TS_TRACE(2 + 8 * x + 3);
+      // Row hand-off, both sides off the critical path.  Writer: the lanes of CTA 0 that stored the rows of
+      // the SNPs before this one fence AFTER this arrival (the fence overlaps the barrier wait that follows
+      // and precedes CTA 0's next arrival).  Reader: the helper warp fences in round 0's wait and prepares
+      // the next SNP's round-0 b in round 1's wait, while the other warps sit in front of sync2.
+      if (x == 0) {
+        if (blockIdx.x == 0 && tid < V && (i % (RING / 2)) == 0 && i > 0) fence_gpu();
+        if (warp == W - 1 && can_prepare && i + 1 < n_items) fence_gpu();
+      } else if (x == 1) {
+        prepare_next();
+        next_prepared = true;
+      }
       // The last round's totals only feed lambda[loc] (the gamma step uses the phi of THIS E-step),
       // so when this round is known to be the last one the gamma step runs now, in the shadow of
       // the grid barrier, and the control warp collects the totals afterwards.
       if (x + 1 >= p.max_rounds && !(it.flags & ITEM_HOL)) {
-        prepare_next();
         gamma_step(bx);
         gamma_done = true;
       }
@@ -603,15 +701,10 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
           chg = warp_sum(chg);
           done = chg / (double)V < p.thresh;
         }
-        if (done) {  // the finished row: into this CTA's ring, and (CTA 0) to global memory
-          const int slot = (int)(i % RING);
-          if (lane < RING && (lane == slot || s_ring_loc[lane] == it.loc)) s_ring_loc[lane] = lane == slot ? it.loc : 0xffffffffu;
+        if (done && blockIdx.x == 0) {  // the finished row to global memory; every CTA keeps it in `lam` for its ring
 #pragma unroll
           for (int q = 0; q < VPL; ++q)
-            if (lane + 32 * q < V) {
-              s_ring[slot * V + lane + 32 * q] = own[q];
-              if (blockIdx.x == 0) st_row(p.lambda + (size_t)it.loc * V + lane + 32 * q, own[q]);
-            }
+            if (lane + 32 * q < V) st_row(p.lambda + (size_t)it.loc * V + lane + 32 * q, own[q]);
         }
         if (lane == 0) {
           if (abort) { st->fault = 1; *s_flag = 2; }
@@ -631,10 +724,8 @@ __global__ void __launch_bounds__(persist_tmax(K, I), 1) k_persist(Params p, uin
 
     // early-converged SNPs take the gamma step here; the usual case (all rounds run) took it
     // inside the last round, in the shadow of that round's grid barrier
-    if (!gamma_done) {
-      prepare_next();
-      if (!(it.flags & ITEM_HOL)) gamma_step(x == 1 ? b_first : s_b + ((x - 1) & 1) * V);
-    }
+    if (!next_prepared) prepare_next();  // the SNP ended after its first round
+    if (!gamma_done && !(it.flags & ITEM_HOL)) gamma_step(x == 1 ? b_first : s_b + ((x - 1) & 1) * V);
     TS_TRACE(100);
     __syncthreads();  // s_b is rewritten for the next SNP
     TS_TRACE(101);

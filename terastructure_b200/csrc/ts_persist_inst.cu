@@ -8,69 +8,74 @@
 #define TS_CAT(a, b) TS_CAT2(a, b)
 #define TS_RANGE_FN TS_CAT(ts_launch_persist_k, TS_KLO)
 
-template <int K, int I>
+template <int K, int I, bool TIER>
 static cudaError_t launch_ki(const Params &prm, uint32_t n_items, int grid, int block, cudaStream_t stream) {
-  if constexpr (I > tsp::persist_imax(K) && I != 0) {
+  if constexpr (I > tsp::persist_imax(K) || (TIER && I != tsp::persist_itier(K))) {
     return cudaErrorInvalidValue;
   } else {
-    const size_t smem = tsp::persist_smem_bytes(K, I);
+    const size_t smem = tsp::persist_smem_bytes(K, TIER ? tsp::TIER_THREADS : tsp::persist_tmax(K, I)) +
+                        (TIER ? (size_t)prm.tier_j * tsp::persist_tier_slot_bytes(K) : 0);
     // Set once per device: cudaFuncSetAttribute can serialise behind a running kernel, and a
     // peer's kernel may be spinning on the one this call is about to launch.
-    static bool attr_set[64] = {false};
+    static size_t attr_set[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (smem > 48 * 1024 && !attr_set[dev & 63]) {
-      cudaError_t er = cudaFuncSetAttribute(tsp::k_persist<K, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024 && attr_set[dev & 63] < smem) {
+      cudaError_t er = cudaFuncSetAttribute(tsp::k_persist<K, I, TIER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (er != cudaSuccess) return er;
-      attr_set[dev & 63] = true;
+      attr_set[dev & 63] = smem;
     }
     Params p = prm;
     void *args[] = {(void *)&p, (void *)&n_items};
-    return cudaLaunchCooperativeKernel((const void *)tsp::k_persist<K, I>, dim3(grid), dim3(block), args, smem, stream);
+    return cudaLaunchCooperativeKernel((const void *)tsp::k_persist<K, I, TIER>, dim3(grid), dim3(block), args, smem, stream);
   }
 }
 
 template <int K>
-static cudaError_t launch_k(int I, const Params &prm, uint32_t n_items, int grid, int block, cudaStream_t stream) {
+static cudaError_t launch_k(int I, bool tier, const Params &prm, uint32_t n_items, int grid, int block, cudaStream_t stream) {
+  if (tier) return I == tsp::persist_itier(K) ? launch_ki<K, tsp::persist_itier(K), true>(prm, n_items, grid, block, stream) : cudaErrorInvalidValue;
   switch (I) {
-    case 0: return launch_ki<K, 0>(prm, n_items, grid, block, stream);
-    case 1: return launch_ki<K, 1>(prm, n_items, grid, block, stream);
-    case 2: return launch_ki<K, 2>(prm, n_items, grid, block, stream);
-    case 3: return launch_ki<K, 3>(prm, n_items, grid, block, stream);
-    case 4: return launch_ki<K, 4>(prm, n_items, grid, block, stream);
+    case 1: return launch_ki<K, 1, false>(prm, n_items, grid, block, stream);
+    case 2: return launch_ki<K, 2, false>(prm, n_items, grid, block, stream);
+    case 3: return launch_ki<K, 3, false>(prm, n_items, grid, block, stream);
+    case 4: return launch_ki<K, 4, false>(prm, n_items, grid, block, stream);
   }
   return cudaErrorInvalidValue;
 }
 
 template <int K>
-static cudaError_t launch_from(int k, int I, const Params &prm, uint32_t n_items, int grid, int block, cudaStream_t stream) {
+static cudaError_t launch_from(int k, int I, bool tier, const Params &prm, uint32_t n_items, int grid, int block, cudaStream_t stream) {
   if constexpr (K > TS_KHI) {
     return cudaErrorInvalidValue;
   } else {
-    if (k == K) return launch_k<K>(I, prm, n_items, grid, block, stream);
-    return launch_from<K + 1>(k, I, prm, n_items, grid, block, stream);
+    if (k == K) return launch_k<K>(I, tier, prm, n_items, grid, block, stream);
+    return launch_from<K + 1>(k, I, tier, prm, n_items, grid, block, stream);
   }
 }
 
-cudaError_t TS_RANGE_FN(int K, int I, const Params &prm, uint32_t n_items, int grid, int block, cudaStream_t stream) {
-  return launch_from<TS_KLO>(K, I, prm, n_items, grid, block, stream);
+cudaError_t TS_RANGE_FN(int K, int I, bool tier, const Params &prm, uint32_t n_items, int grid, int block, cudaStream_t stream) {
+  return launch_from<TS_KLO>(K, I, tier, prm, n_items, grid, block, stream);
 }
 
 #ifdef TS_PERSIST_MAIN
-cudaError_t ts_launch_persist_k5(int, int, const Params &, uint32_t, int, int, cudaStream_t);
-cudaError_t ts_launch_persist_k9(int, int, const Params &, uint32_t, int, int, cudaStream_t);
-cudaError_t ts_launch_persist_k13(int, int, const Params &, uint32_t, int, int, cudaStream_t);
-cudaError_t ts_launch_persist_k17(int, int, const Params &, uint32_t, int, int, cudaStream_t);
-cudaError_t ts_launch_persist_k21(int, int, const Params &, uint32_t, int, int, cudaStream_t);
+cudaError_t ts_launch_persist_k5(int, int, bool, const Params &, uint32_t, int, int, cudaStream_t);
+cudaError_t ts_launch_persist_k9(int, int, bool, const Params &, uint32_t, int, int, cudaStream_t);
+cudaError_t ts_launch_persist_k13(int, int, bool, const Params &, uint32_t, int, int, cudaStream_t);
+cudaError_t ts_launch_persist_k17(int, int, bool, const Params &, uint32_t, int, int, cudaStream_t);
+cudaError_t ts_launch_persist_k21(int, int, bool, const Params &, uint32_t, int, int, cudaStream_t);
 
-cudaError_t ts_launch_persist(int K, int I, const Params &prm, uint32_t n_items, int grid, int block, cudaStream_t stream) {
-  if (K <= 4) return ts_launch_persist_k1(K, I, prm, n_items, grid, block, stream);
-  if (K <= 8) return ts_launch_persist_k5(K, I, prm, n_items, grid, block, stream);
-  if (K <= 12) return ts_launch_persist_k9(K, I, prm, n_items, grid, block, stream);
-  if (K <= 16) return ts_launch_persist_k13(K, I, prm, n_items, grid, block, stream);
-  if (K <= 20) return ts_launch_persist_k17(K, I, prm, n_items, grid, block, stream);
-  return ts_launch_persist_k21(K, I, prm, n_items, grid, block, stream);
+cudaError_t ts_launch_persist(int K, int I, bool tier, const Params &prm, uint32_t n_items, int grid, int block, cudaStream_t stream) {
+  if (K <= 4) return ts_launch_persist_k1(K, I, tier, prm, n_items, grid, block, stream);
+  if (K <= 8) return ts_launch_persist_k5(K, I, tier, prm, n_items, grid, block, stream);
+  if (K <= 12) return ts_launch_persist_k9(K, I, tier, prm, n_items, grid, block, stream);
+  if (K <= 16) return ts_launch_persist_k13(K, I, tier, prm, n_items, grid, block, stream);
+  if (K <= 20) return ts_launch_persist_k17(K, I, tier, prm, n_items, grid, block, stream);
+  return ts_launch_persist_k21(K, I, tier, prm, n_items, grid, block, stream);
 }
 int ts_persist_imax(int K) { return tsp::persist_imax(K); }
+int ts_persist_itier(int K) { return tsp::persist_itier(K); }
 int ts_persist_tmax(int K, int I) { return tsp::persist_tmax(K, I); }
+int ts_persist_tier_threads(void) { return tsp::TIER_THREADS; }
+size_t ts_persist_smem_base(int K, int threads) { return tsp::persist_smem_bytes(K, threads); }
+size_t ts_persist_tier_slot_bytes(int K) { return tsp::persist_tier_slot_bytes(K); }
 #endif

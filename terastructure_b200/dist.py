@@ -14,10 +14,12 @@ _keepalive = []  # symmetric buffers must outlive the engines that use them
 def connect(engine, group=None):
     """Connect `engine` (rank, nranks as created) with its peers in `group` (default: WORLD).
 
-    Preferred: a torch symmetric-memory buffer with an NVLS multicast alias -> in-switch reduction
-    (ts_comm_attach_symmetric).  Otherwise, or with TSGPU_XCHG=ipc: CUDA-IPC handles of the engines'
-    own buffers and peer stores (ts_comm_export / ts_comm_connect).  Returns a dict describing what
-    was set up; ends with a barrier, so ts_steps may follow immediately."""
+    Default: CUDA-IPC handles of the engines' own exchange buffers and peer stores over NVLink
+    (ts_comm_export / ts_comm_connect) -- the fastest scheme measured (profiles/r2_summary.md).
+    TSGPU_XCHG=slots|mcslot|mcred: a torch symmetric-memory buffer, optionally with its NVLS multicast
+    alias (ts_comm_attach_symmetric): one multicast store of the GPU totals, or the in-switch reduction
+    with multimem.red from every CTA.  Returns a dict describing what was set up; ends with a barrier,
+    so ts_steps may follow immediately."""
     import torch
     import torch.distributed as dist
     group = group or dist.group.WORLD
@@ -26,7 +28,7 @@ def connect(engine, group=None):
     if world == 1:
         return info
     want = os.environ.get("TSGPU_XCHG", "")
-    if want != "ipc":
+    if want in ("slots", "mcslot", "mcred"):
         import torch.distributed._symmetric_memory as symm_mem
         dev = torch.device("cuda", int(engine.cfg.device))
         nbytes = int(capi.lib().ts_comm_state_bytes())

@@ -237,16 +237,21 @@ def test_shard_plan_geometry():
     assert ts.plan_shard(100000, 10, sms) == (3, 148, 256)      # BASELINE configs[2] on one B200
     assert ts.plan_shard(125000, 10, sms) == (4, 148, 224)      # configs[3] over 8 GPUs
     assert ts.plan_shard(60000, 10, sms)[0] == 2 and ts.plan_shard(80000, 10, sms)[0] == 3
-    assert ts.plan_shard(400000, 10, sms)[0] == 0               # streaming variant
     assert ts.plan_shard(200, 3, sms) == (1, 4, 64)             # the reference's bundled data set
+    # beyond the register-resident capacity: 2 individuals per thread in registers, more in shared memory
+    assert ts.plan_shard(400000, 10, sms) == (2, 148, 256) and ts.plan_tiers(400000, 10, sms) == (9, 0)
+    j, streamed = ts.plan_tiers(1_000_000, 10, sms)
+    assert j == 11 and streamed == 1_000_000 - 13 * 148 * 256   # 227 KB of shared memory per CTA hold 11 more
+    assert ts.plan_tiers(100000, 10, sms) == (0, 0)
     for k in (1, 2, 6, 10, 12, 13, 16, 20, 21, 32):
         for n in (1, 3, 31, 33, 200, 4097, 9999, 37888, 37889, 56000, 75776, 99999, 113664, 113665, 151552, 151553, 10 ** 6):
             ipt, grid, block = ts.plan_shard(n, k, sms)
+            j, streamed = ts.plan_tiers(n, k, sms)
             assert 1 <= grid <= sms and block % 32 == 0 and 32 <= block <= 512
-            if ipt:
-                assert 1 <= ipt <= 4 and grid * block * ipt >= n, (k, n, ipt, grid, block)
-            else:
-                assert grid == sms
+            assert 1 <= ipt <= 4 and 0 <= j <= 16
+            assert grid * block * (ipt + j) + streamed >= n, (k, n, ipt, grid, block, j, streamed)
+            if streamed:
+                assert grid * block * (ipt + j) + streamed == n and grid == sms
     with pytest.raises(ts.TsError):
         ts.plan_shard(100, 33, sms)
 
