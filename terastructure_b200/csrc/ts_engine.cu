@@ -12,12 +12,16 @@
 //   cnt    [npad]          per-individual step counts (_c_indiv, snpsamplinge.cc:688-693)
 //   lambda [L][K][2]       fp64; Ebeta/Elogbeta are derived from it on the fly
 //
-// Kernels per SVI iteration (all on the engine's stream, no host round trip):
+// Kernels (all on the engine's stream, no host round trip):
+//   tsp::k_persist<K, I, TIER>   a whole batch of SVI iterations in one cooperative launch (ts_persist.cuh)
+//   k_heldout<K>                 held-out log-likelihood of one validation locus          (hol mode)
+// TEST-ONLY build (-DTS_STAGED_PATH, lib/libtsgpu_staged.so, never the product library): the first
+// correct path, one launch per round, kept as an independent implementation of the same mathematics
+// that tests/ cross-check the persistent kernel against (TSGPU_PATH=staged):
 //   k_begin            1 CTA: advance the work cursor, b[k][t] = exp(Elogbeta[loc][k][t])
 //   k_estep<K> x I     E-step + fp64 sufficient-statistic reduction + lambda update; later
 //                      launches return immediately once the round loop has converged
 //   k_gamma<K>         gamma natural-gradient step + exp(psi(gamma)) refresh   (training)
-//   k_heldout<K>       held-out log-likelihood of one validation locus          (hol mode)
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -60,6 +64,7 @@ static int set_err(int code, const char *fmt, ...) {
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
+#ifdef TS_STAGED_PATH
 constexpr int ESTEP_THREADS = 256;
 
 // b[k][t] = exp(psi(lambda[k][t]) - psi(lambda[k][0]+lambda[k][1]))  (estimate_beta, cc:279-296)
@@ -283,6 +288,8 @@ __global__ void __launch_bounds__(256) k_gamma(Params p) {
     }
   }
 }
+
+#endif  // TS_STAGED_PATH
 
 // snp_likelihood (hh:322-361): one CTA per work item (= validation locus).  gamma does not
 // change during a held-out pass and every locus owns its lambda row, so the whole pass is
@@ -518,6 +525,7 @@ static void fill_params(ts_engine *e) {
   X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) \
   X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(29) X(30) X(31) X(32)
 
+#ifdef TS_STAGED_PATH
 static void launch_estep(ts_engine *e) {
   switch (e->K) {
 #define X(k) \
@@ -534,6 +542,7 @@ static void launch_gamma(ts_engine *e) {
 #undef X
   }
 }
+#endif
 static void launch_heldout(ts_engine *e, unsigned n_items) {
   switch (e->K) {
 #define X(k) \
@@ -745,14 +754,23 @@ int ts_create(const ts_config *cfg, ts_engine **out) {
   CKE(cudaMemsetAsync(e->ctl, 0, sizeof(Ctl), e->stream));
   CKE(cudaMemsetAsync(e->xchg, 0, sizeof(Xchg), e->stream));
   // Grid sizing: whole CTAs of individuals, capped at two CTAs per SM.
+#ifdef TS_STAGED_PATH
   const int need = (int)((cfg->n_local + ESTEP_THREADS - 1) / ESTEP_THREADS);
   e->grid_estep = std::max(1, std::min(need, e->num_sms));
   e->grid_gamma = std::max(1, std::min(need, 4 * e->num_sms));
+#endif
   {
     // Persistent kernel: one CTA per SM at most, threads sized so that every thread owns the
     // same number of individuals (I = ceil(n / (SMs * TMAX))).
     const char *path = getenv("TSGPU_PATH");
     e->staged = path && !strcmp(path, "staged");
+#ifndef TS_STAGED_PATH
+    if (e->staged) {
+      set_err(TS_ERR_STATE, "TSGPU_PATH=staged needs the test-only library lib/libtsgpu_staged.so (make staged); the product library has no staged path");
+      ts_destroy(e);
+      return TS_ERR_STATE;
+    }
+#endif
     // test/developer knobs: TSGPU_IPT pins the individuals per thread in registers (0 = the TIER kernel);
     // TSGPU_TIER_J / TSGPU_TIER_GRID / TSGPU_TIER_BLOCK shape the TIER kernel so that the parity tests
     // reach its shared-memory and streaming tiers at sizes the oracle finishes in seconds
@@ -1046,7 +1064,9 @@ static int run_items(ts_engine *e, const std::vector<WorkItem> &items, uint32_t 
   } else if (!e->staged) {
     CK(launch_persist(e, (uint32_t)n));
     e->launches++;
-  } else {
+  }
+#ifdef TS_STAGED_PATH
+  else {
     const long long minus1 = -1;
     CK(cudaMemcpyAsync(&e->ctl->cursor, &minus1, sizeof(long long), cudaMemcpyHostToDevice, e->stream));
     for (size_t i = 0; i < n; ++i) {
@@ -1062,6 +1082,7 @@ static int run_items(ts_engine *e, const std::vector<WorkItem> &items, uint32_t 
       }
     }
   }
+#endif
   if (hol) {
     launch_heldout(e, (unsigned)n);
     e->launches++;

@@ -113,6 +113,21 @@ TSFX_HD double to_double(unsigned long long hi, unsigned long long lo, const Uns
   return dh + dl;
 }
 
+// lambda = eta + S in one rounding: eta (a small integer-valued prior count, a multiple of 2^-sh) is
+// folded into the high word's offset -- hi * 2^-sh + eta is exactly representable (< 2^53 units of 2^-sh),
+// so the only rounding is the final addition of the low word's part.  One dependent FP64 instruction
+// less on the round's critical path than eta + to_double(...), and one rounding less.
+TSFX_HD double to_double_plus(unsigned long long hi, unsigned long long lo, const Unscale &u, double eta) {
+#if defined(__CUDA_ARCH__)
+  const double dh = fma(double_of((long long)(hi | 0x4330000000000000ull)), u.hi_inv, u.hi_off + eta);
+  const double dl = fma(double_of((long long)(lo | 0x4330000000000000ull)), u.lo_inv, u.lo_off);
+#else
+  const double dh = double_of((long long)(hi | 0x4330000000000000ull)) * u.hi_inv + (u.hi_off + eta);
+  const double dl = double_of((long long)(lo | 0x4330000000000000ull)) * u.lo_inv + u.lo_off;
+#endif
+  return dh + dl;
+}
+
 // 2^sh for a data set of n_total individuals: every statistic is at most 2 n_total.
 TSFX_HD int shift_for(unsigned long long n_total) {
   int bits = 1;

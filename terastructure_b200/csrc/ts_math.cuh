@@ -42,5 +42,7 @@ __device__ __forceinline__ int plink_code(const unsigned char *col, unsigned lon
   return (col[n >> 2] >> (2 * (unsigned)(n & 3))) & 3;
 }
 __device__ __forceinline__ int code_to_y(int code) { return code - (code >> 1); }
+// (double)w for w in {0, 1, 2} through the exponent field: 1.0 = 0x3FF00000'00000000, 2.0 = 0x40000000'00000000
+__device__ __forceinline__ double weight_of(int w) { return __hiloint2double(w ? 0x3FE00000 + (w << 20) : 0, 0); }
 
 }  // namespace tsm

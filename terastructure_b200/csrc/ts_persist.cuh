@@ -40,6 +40,12 @@
 #define TS_OPTS 0
 #endif
 #define TS_OPT_NOFENCE ((TS_OPTS) & 8)
+#ifndef TS_TIER_UNROLL  // individuals of the shared-memory / streaming tiers in flight per thread (K <= 12)
+#define TS_TIER_UNROLL 2
+#endif
+#ifndef TS_TIER_I       // individuals per thread in registers in the TIER kernels (K <= 12)
+#define TS_TIER_I 2
+#endif
 
 namespace tsp {
 
@@ -169,7 +175,7 @@ constexpr int RING = 8;
 // Individual n = m * (grid x T) + global thread id; m < I: registers, m < I + J: shared, else global.
 // Threads per CTA are capped so that the register file holds the register tier without spills.
 __host__ __device__ constexpr int persist_imax(int K) { return K <= 12 ? 4 : (K <= 20 ? 3 : 1); }
-__host__ __device__ constexpr int persist_itier(int K) { return K <= 12 ? 2 : 1; }  // register tier of the TIER kernels
+__host__ __device__ constexpr int persist_itier(int K) { return K <= 12 ? TS_TIER_I : 1; }  // register tier of the TIER kernels
 constexpr int TIER_THREADS = 256;
 constexpr int TIER_JMAX = 16;  // codes of the shared-memory tier travel as 2 bits each in one register
 __host__ __device__ constexpr int persist_tmax(int K, int I) {
@@ -220,6 +226,7 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
   constexpr int NW = 2 * V;           // fixed-point words per round: word = hl * V + v
   constexpr int VPL = (V + 31) / 32;  // statistics per lane of the control warp
   constexpr int TM = TIER ? TIER_THREADS : persist_tmax(K, I);
+  constexpr int TIER_UNROLL = K <= 12 ? TS_TIER_UNROLL : 1;  // tier individuals in flight per thread, while registers allow
   constexpr int WS = TM / 32 + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *s_b = reinterpret_cast<double *>(smem_raw);                // [2][V]: b of round x >= 1 at [x&1]
@@ -260,6 +267,9 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
   }
   uint32_t prev_loc = 0xffffffffu;
   if (tid < RING) s_ring_loc[tid] = 0xffffffffu;
+  // slots of warps this CTA does not have stay zero, so the CTA sum below adds all WS - 1 slots
+  // unconditionally (straight-line vector loads instead of a predicated chain)
+  for (int idx = tid; idx < NW * WS; idx += blockDim.x) s_fix[idx] = 0;
 
   // this thread's individuals and their E = exp(psi(gamma)) rows: register tier
   constexpr int IR = I;
@@ -338,9 +348,7 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
         const int v = lane + 32 * q;
         const double other = __shfl_xor_sync(0xffffffffu, own[q], 1);
         const double l0 = (v & 1) ? other : own[q], l1 = (v & 1) ? own[q] : other;
-        double s = 0.0;
-        s += l0;
-        s += l1;
+        const double s = l0 + l1;  // the reference adds 0 + l0 + l1 (cc:283-286): 0 + l0 is exact
         const double b = f_expsi(own[q]) * fast_rcp(f_expsi(s));
         if (v < V) { dst[v] = b; row_dst[v] = own[q]; }
       }
@@ -374,9 +382,7 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
           const int v = lane + 32 * q;
           const double other = __shfl_xor_sync(0xffffffffu, lam[q], 1);
           const double l0 = (v & 1) ? other : lam[q], l1 = (v & 1) ? lam[q] : other;
-          double s = 0.0;
-          s += l0;
-          s += l1;
+          const double s = l0 + l1;  // the reference adds 0 + l0 + l1 (cc:283-286): 0 + l0 is exact
           const double b = f_expsi(lam[q]) * fast_rcp(f_expsi(s));
           if (v < V) b_first[v] = b;
         }
@@ -426,8 +432,8 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
       const int y = tsm::code_to_y(c);
       double s0, s1;
       dot_b<K, true>(en, bl, s0, s1);
-      q0 = (double)y * fast_rcp1(s0);
-      q1 = (double)(2 - y) * fast_rcp1(s1);
+      q0 = tsm::weight_of(y) * fast_rcp1(s0);
+      q1 = tsm::weight_of(2 - y) * fast_rcp1(s1);
     };
     auto gamma_step = [&](const double *bl) {
 #pragma unroll
@@ -488,8 +494,8 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
       for (int v = 0; v < V; ++v) vv[v] = 0.0;
       auto estep_one = [&](auto split, int c, bool ok, const double (&en)[K], double &q0, double &q1) {
         // missing or held out (kv_ok, hh:389-408) -> weight 0; branch-free, the warp stays converged
-        const int y = tsm::code_to_y(c);
-        const double w0 = (c == 1) ? 0.0 : (double)y, w1 = (c == 1) ? 0.0 : (double)(2 - y);
+        // weights y and 2 - y built from the code's bits (no I2F.F64 in the round loop): codes 0, 2, 3 = y 0, 1, 2
+        const double w0 = tsm::weight_of(c == 1 ? 0 : tsm::code_to_y(c)), w1 = tsm::weight_of(c == 1 ? 0 : 2 - tsm::code_to_y(c));
         double s0, s1;
         dot_b<K, decltype(split)::value>(en, bx, s0, s1);
         // padding threads (no individual) have e = 0, s = 0: keep the reciprocal finite
@@ -504,14 +510,14 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
 #pragma unroll
       for (int j = 0; j < I; ++j) estep_one(std::false_type{}, code[j], valid[j], e[j], r0[j], r1[j]);
       if constexpr (TIER) {
-#pragma unroll(K <= 12 ? 2 : 1)
+#pragma unroll(TIER_UNROLL)
         for (int j = 0; j < J; ++j) {  // shared-memory tier, two individuals in flight while registers allow
           double en[K], q0, q1;
 #pragma unroll
           for (int k = 0; k < K; ++k) en[k] = s_E[(size_t)(j * K + k) * T + tid];
           estep_one(std::true_type{}, (scode >> (2 * j)) & 3, tier_n(j) < p.n_local, en, q0, q1);
         }
-#pragma unroll(K <= 12 ? 2 : 1)
+#pragma unroll(TIER_UNROLL)
         for (uint32_t n = stream_begin + gtid; n < p.n_local; n += GT) {  // streaming tier: E from L2/HBM
           double en[K], q0, q1;
 #pragma unroll
@@ -542,8 +548,7 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
         const long long *sh = s_fix + v * WS, *sl = s_fix + (V + v) * WS;
         long long hi = 0, lo = 0;
 #pragma unroll
-        for (int ww = 0; ww < WS - 1; ++ww)
-          if (ww < W) { hi += sh[ww]; lo += sl[ww]; }
+        for (int ww = 0; ww < WS - 1; ++ww) { hi += sh[ww]; lo += sl[ww]; }
         tsfx::normalize(hi, lo);  // the low word becomes [0, 2^44)
         if (p.xmode == XMODE_MCRED) {  // in-switch: one arrival per CTA on EVERY GPU's copy of the word
           mm_red_add(&p.pst_mc->acc[par][v][0], (unsigned long long)hi + (1ull << tsfx::MC_CNT_SHIFT));
@@ -657,7 +662,8 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
               tsfx::fold(dh, dl);  // the ranks' low words can add up to 2^52 and more: carry first
             }
           }
-          tot[q] = tsfx::to_double(dh, dl, fxu);  // u64 -> double through the mantissa (both < 2^52)
+          // update_lambda (cc:267-277): lambda = eta + S, u64 -> double through the mantissa (both words < 2^52)
+          tot[q] = tsfx::to_double_plus(dh, dl, fxu, (v & 1) ? p.eta1 : p.eta0);
         }
         TS_TRACE(2 + 8 * x + 4);
         // new lambda -> new b first (the critical path of the round); convergence test afterwards
@@ -667,15 +673,13 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
         for (int q = 0; q < VPL; ++q) {
           const int v = lane + 32 * q;
           oldlam[q] = lam[q];
-          own[q] = (v < V) ? ((v & 1) ? p.eta1 : p.eta0) + tot[q] : 1024.0;  // update_lambda (cc:267-277); idle lanes: any large value
+          own[q] = (v < V) ? tot[q] : 1024.0;  // idle lanes: any large value
           lam[q] = own[q];
           if (x + 1 < p.max_rounds) {  // the last permitted round has no successor that would read b
             const double fo = f_expsi(own[q]);
             const double other = __shfl_xor_sync(0xffffffffu, own[q], 1);
             const double l0 = (v & 1) ? other : own[q], l1 = (v & 1) ? own[q] : other;
-            double s = 0.0;
-            s += l0;
-            s += l1;
+            const double s = l0 + l1;  // the reference adds 0 + l0 + l1 (cc:283-286): 0 + l0 is exact
             const double b = fo * fast_rcp(f_expsi(s));  // estimate_beta (cc:279-296)
             if (v < V) bn[v] = b;
           }

@@ -4,6 +4,12 @@
 #include "ts_device.cuh"
 #include "ts_persist.cuh"
 
+#ifndef TS_KMIN  // developer builds (tools/dev/ab.sh) instantiate a sub-range of K only: smaller, faster to build and ship
+#define TS_KMIN 1
+#endif
+#ifndef TS_KMAX
+#define TS_KMAX 32
+#endif
 #define TS_CAT2(a, b) a##b
 #define TS_CAT(a, b) TS_CAT2(a, b)
 #define TS_RANGE_FN TS_CAT(ts_launch_persist_k, TS_KLO)
@@ -48,7 +54,10 @@ static cudaError_t launch_from(int k, int I, bool tier, const Params &prm, uint3
   if constexpr (K > TS_KHI) {
     return cudaErrorInvalidValue;
   } else {
-    if (k == K) return launch_k<K>(I, tier, prm, n_items, grid, block, stream);
+    if (k == K) {
+      if constexpr (K >= TS_KMIN && K <= TS_KMAX) return launch_k<K>(I, tier, prm, n_items, grid, block, stream);
+      else return cudaErrorInvalidValue;  // a developer build restricted to some K (make KMIN=.. KMAX=..)
+    }
     return launch_from<K + 1>(k, I, tier, prm, n_items, grid, block, stream);
   }
 }

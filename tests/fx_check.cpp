@@ -145,6 +145,19 @@ int main() {
     // at most 3 units of 2^-44 dropped per CTA
     REQUIRE(fabsl((long double)got - ref) <= std::ldexp((long double)(4 * ranks * ctas), -44 - sh) + fabsl(ref) * 1.2e-16L);
   }
+  // lambda = eta + S with eta folded into the high word's offset: equals the exact value rounded once
+  {
+    const int sh = tsfx::shift_for(1000000);
+    const tsfx::Unscale u = tsfx::unscale(std::ldexp(1.0, -sh));
+    for (int it = 0; it < 100000; ++it) {
+      const unsigned long long hi = (unsigned long long)(U(g) * 4.4e15) & ((1ull << 52) - 1), lo = (unsigned long long)(U(g) * 1.7e13) & ((1ull << 44) - 1);
+      const double eta = (it & 1) ? 1.0 : 3.0;
+      const long double exact = (long double)eta + std::ldexp((long double)hi, -sh) + std::ldexp((long double)lo, -sh - 44);
+      const double got = tsfx::to_double_plus(hi, lo, u, eta);
+      REQUIRE((long double)got == (long double)(double)exact || fabsl((long double)got - exact) <= fabsl(exact) * 1.2e-16L);
+      REQUIRE(fabsl((long double)got - exact) <= fabsl((long double)(eta + tsfx::to_double(hi, lo, u)) - exact) + fabsl(exact) * 1e-19L);
+    }
+  }
   printf("ok\n");
   return 0;
 }

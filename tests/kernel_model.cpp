@@ -72,7 +72,7 @@ extern "C" int km_train(uint32_t n, uint32_t l, uint32_t k, const uint8_t *y /* 
       double chg = 0.0;
       for (uint32_t v = 0; v < V; ++v) {
         tsfx::normalize(hi_tot[v], lo_tot[v]);
-        const double own = eta + tsfx::to_double((unsigned long long)hi_tot[v], (unsigned long long)lo_tot[v], fxu);
+        const double own = tsfx::to_double_plus((unsigned long long)hi_tot[v], (unsigned long long)lo_tot[v], fxu, eta);  // as the kernel
         chg += std::fabs(own - lam[v]);
         lam[v] = own;
       }

@@ -325,21 +325,41 @@ def test_cli_drop_in(tmp_path):
     assert r.returncode != 0 and "already exists" in r.stderr
 
 
-def test_staged_path_matches_persistent(monkeypatch):
-    """TSGPU_PATH=staged runs one launch per round (the simple cross-check path); the default
-    persistent kernel must agree with it to rounding on a trajectory with reports."""
+def _staged(*args):
+    """Run tests/staged_helper.py (the staged path lives in the test-only library) and load its dump."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    from conftest import ROOT
+    out = os.path.join(tempfile.mkdtemp(prefix="tsstaged."), "out.npz")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "staged_helper.py"), *[str(a) for a in args], out],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return np.load(out)
+
+
+def test_staged_path_matches_persistent():
+    """The staged path (one launch per round, test-only library) is an independent implementation of the
+    same mathematics: the persistent kernel must agree with it to rounding on a trajectory with reports."""
     c = load_case("synthA")
     last = int(c["gold"]["val_iter"][2])
     s1 = make_driver(c)
     s1.infer(max_iter=last)
+    s2 = _staged("trajectory", "synthA", last)
+    assert [r[0] for r in s1.validation_rows] == s2["val_iter"].tolist()
+    assert np.max(np.abs(np.array([r[2] for r in s1.validation_rows]) - s2["val_ll"])) < 1e-12
+    assert rel_err(s1.engine.gamma, s2["gamma"]) < 1e-11
+    assert rel_err(s1.engine.get_lambda(), s2["lam"]) < 1e-11
+    assert int(s2["launches"]) > 5 * s1.engine.launch_count
+
+
+def test_product_library_has_no_staged_path(monkeypatch):
+    """TSGPU_PATH=staged is refused by the product library (the staged kernels are test infrastructure)."""
+    import terastructure_b200 as ts
     monkeypatch.setenv("TSGPU_PATH", "staged")
-    s2 = make_driver(c)
-    s2.infer(max_iter=last)
-    assert [r[0] for r in s1.validation_rows] == [r[0] for r in s2.validation_rows]
-    assert np.max(np.abs(np.array([r[2] for r in s1.validation_rows]) - np.array([r[2] for r in s2.validation_rows]))) < 1e-12
-    assert rel_err(s1.engine.gamma, s2.engine.gamma) < 1e-11
-    assert rel_err(s1.engine.get_lambda(), s2.engine.get_lambda()) < 1e-11
-    assert s2.engine.launch_count > 5 * s1.engine.launch_count
+    with pytest.raises(ts.TsError, match="test-only library"):
+        ts.Engine(64, 8, 2)
 
 
 def test_exp_digamma_table_on_device():
@@ -406,7 +426,7 @@ def test_cli_012_input_sigterm_and_gpus(tmp_path):
         assert np.all(np.abs(gam - ref) <= 1e-6 * np.abs(ref) + 1.01e-8), it
 
 
-def test_large_shard_tiered_kernel(monkeypatch):
+def test_large_shard_tiered_kernel():
     """Shards beyond the register-resident capacity (148 CTAs x 256 threads x 4 individuals at
     K <= 12) run the tiered persistent kernel (registers + shared memory, here all on chip):
     same invariants, and agreement with the staged path on the same inputs."""
@@ -416,28 +436,23 @@ def test_large_shard_tiered_kernel(monkeypatch):
     theta, beta = synth.psd_params(n, l, k, seed=2)
     g0 = np.random.RandomState(1).gamma(100.0, 0.01, size=(n, k))
     locs = np.array([3, 9, 3, 5], np.uint32)
-
-    def run():
-        e = ts.Engine(n, l, k)
-        e.synth_bed(7, theta, beta, 0.01)
-        e.set_gamma(g0)
-        before = e.launch_count
-        rounds = e.steps(locs, want_rounds=True)
-        return e, rounds, e.launch_count - before
-
-    e, rounds, launches = run()
-    assert np.all(rounds == 10) and launches == 1            # one persistent launch for the batch
+    e = ts.Engine(n, l, k)
+    e.synth_bed(7, theta, beta, 0.01)
+    e.set_gamma(g0)
+    before = e.launch_count
+    rounds = e.steps(locs, want_rounds=True)
+    assert np.all(rounds == 10) and e.launch_count - before == 1    # one persistent launch for the batch
+    assert e.tiers[0] >= 1 and e.tiers[1] == 0                       # shared-memory tier in use, nothing streams
     for loc in (3, 9, 5):
         y = plink.unpack(e.get_bed_row(loc)[None, :], n)[0]
         ok = y != 3
         lam = e.get_lambda(loc, 1)[0]
         assert abs(lam[:, 0].sum() - k - y[ok].sum()) < 1e-7 * n
         assert abs(lam[:, 1].sum() - k - (2 - y[ok].astype(np.int64)).sum()) < 1e-7 * n
-    monkeypatch.setenv("TSGPU_PATH", "staged")
-    e2, rounds2, launches2 = run()
-    assert launches2 >= len(locs) * 11                       # one launch per round
-    assert rel_err(e.gamma, e2.gamma) < 1e-11 and rel_err(e.get_lambda(), e2.get_lambda()) < 1e-11
-    np.testing.assert_array_equal(e.counts, e2.counts)
+    s2 = _staged("steps", n, l, k, 2, 7, 0.01, 1, ",".join(str(x) for x in locs))
+    assert int(s2["launches"]) >= len(locs) * 11                     # one launch per round
+    assert rel_err(e.gamma, s2["gamma"]) < 1e-11 and rel_err(e.get_lambda(), s2["lam"]) < 1e-11
+    np.testing.assert_array_equal(e.counts, s2["counts"])
 
 
 def test_run_to_run_determinism():
