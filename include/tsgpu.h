@@ -88,8 +88,8 @@ int ts_destroy(ts_engine *e);
  * 2-bit packed in HBM (codes 00->0, 10->1, 11->2, 01->missing, snp.cc:203-216). */
 int ts_load_bed(ts_engine *e, uint64_t loc_begin, uint64_t nloc, const uint8_t *rows,
                 uint64_t row_pitch);
-/* The same for all engines of one process in ONE pass over the rows (the CLI's -gpus N; rows is
- * typically a memory-mapped .bed of up to 250 GB): chunks are staged through pinned host buffers and
+/* The same for all engines of one process in ONE pass over the rows (the CLI's -gpus N; `rows` points at
+ * the row of locus loc_begin, typically inside a memory-mapped .bed of up to 250 GB): chunks are staged through pinned host buffers and
  * every engine copies its own byte range asynchronously while the next chunk is read.  Returns when
  * all engines hold their shards. */
 int ts_load_bed_fanout(ts_engine **engines, int n, uint64_t loc_begin, uint64_t nloc, const uint8_t *rows,
@@ -179,16 +179,19 @@ int ts_comm_connect_local(ts_engine **engines, int n);
  * rank_ptrs[nranks] (rank order, own rank included) and, optionally, a multicast pointer that
  * aliases the same offsets of ALL ranks' buffers (e.g. torch.distributed._symmetric_memory:
  * empty() + rendezvous() give buffer_ptrs and multicast_ptr).  The engine's exchange state moves into
- * its own buffer.  The scheme is chosen by TSGPU_XCHG in the environment: unset or "slots" = peer
- * stores as with ts_comm_connect (the fastest measured, profiles/r2_summary.md); "mcslot" = CTA 0
- * publishes the GPU totals with ONE multicast store (multimem.st); "mcred" = in-switch reduction,
- * every CTA of every rank adds its words with multimem.red.  Call it on every rank, then
+ * its own buffer.  Exchange schemes (ts_comm_mode; TSGPU_XCHG in the environment forces one): with a
+ * multicast pointer the default is "mcacc" -- CTA 0 adds the GPU's totals into an accumulator on every rank
+ * with ONE multimem.red per word, every CTA polls one local word pair; without, "gacc" -- the same with one
+ * NVLink red.add per peer (also what ts_comm_connect uses).  "slots" = the round-1 slot exchange, "mcslot" =
+ * slots written with one multimem.st, "mcred" = multimem.red from every CTA (measurements:
+ * profiles/r2_summary.md).  Call it on every rank, then
  * synchronise the ranks (a host barrier) before the first ts_steps.  total_ctas = sum of the ranks'
- * CTA counts (ts_get_plan), or 0 when all shards have this engine's geometry.  With TSGPU_XCHG=mcslot
- * or mcred, ts_comm_connect_local does all of this by itself for the engines of one process. */
+ * CTA counts (ts_get_plan), or 0 when all shards have this engine's geometry.  ts_comm_connect_local does
+ * all of this by itself for the engines of one process when the devices support multicast. */
 uint64_t ts_comm_state_bytes(void);
 /* Exchange scheme in use: 0 peer stores into slots, 1 NVLS multicast store into slots, 2 NVLS
- * in-switch reduction (multimem.red from every CTA). */
+ * in-switch reduction (multimem.red from every CTA), 3 CTA 0 adds the GPU totals into an accumulator
+ * on every rank with NVLink red.add (the default), 4 the same with one multimem.red per word. */
 int ts_comm_mode(const ts_engine *e);
 int ts_comm_attach_symmetric(ts_engine *e, const void *const *rank_ptrs, void *multicast_ptr, uint64_t bytes,
                              uint32_t total_ctas);

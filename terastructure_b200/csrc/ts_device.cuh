@@ -16,7 +16,10 @@ enum : uint32_t { ITEM_HOL = 1u, ITEM_FIRST = 2u };
 //   SLOTS   CTA 0 stores the GPU's totals into its slot on every peer (unicast NVLink stores)
 //   MCSLOT  the same with ONE multicast store (NVLS): the switch replicates it to every GPU
 //   MCRED   no local stage: every CTA adds its words with multimem.red to every GPU's accumulators
-enum : int { XMODE_SLOTS = 0, XMODE_MCSLOT = 1, XMODE_MCRED = 2 };
+//   GACC    CTA 0 adds the GPU's totals into an accumulator on every rank (one NVLink red.add per peer and
+//           word), every CTA polls ONE local word pair whose count bits count ranks        (the default)
+//   MCACC   the same with ONE multimem.red per word (the switch applies it to every rank's copy)
+enum : int { XMODE_SLOTS = 0, XMODE_MCSLOT = 1, XMODE_MCRED = 2, XMODE_GACC = 3, XMODE_MCACC = 4 };
 
 struct WorkItem {
   const unsigned char *col;  // packed column the E-step/gamma step read (bed row or vcol row)
@@ -59,6 +62,10 @@ struct PState {
   unsigned long long round_ctr;                // rounds run so far (slot tags; same on every rank)
   uint32_t fault;
   uint32_t pad;
+  // XMODE_GACC / XMODE_MCACC: accumulators of the GPUs' totals, replicated on every rank (same layout as acc;
+  // the count bits count ranks), and their totals at the end of the previous launch
+  unsigned long long gacc[2][4 * MAXK][128];
+  unsigned long long gprev[2][4 * MAXK];
 };
 
 // Everything a peer GPU writes into lives in one allocation (one IPC handle).

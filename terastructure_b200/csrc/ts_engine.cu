@@ -556,6 +556,20 @@ static cudaError_t launch_persist(ts_engine *e, uint32_t n_items) {
   return ts_launch_persist(e->K, e->ind_per_thread, e->tier, e->prm, n_items, e->grid_persist, e->block_persist, e->stream);
 }
 
+// How the ranks' totals of a round are exchanged (XMODE_*, ts_device.cuh; measurements in profiles/r2_summary.md:
+// 8 B200s in isolation, cycles per round: slots 8 332, one multimem.st 8 591, replicated accumulator with unicast
+// red.add 5 280 / with one multimem.red 4 947, multimem.red from every CTA 18 673; in the product on 2 B200s, us per
+// SVI iteration: slots 60.1, gacc 51.2, mcacc 48.9).  Default: mcacc where an NVLS alias exists, gacc otherwise.
+// TSGPU_XCHG = gacc | mcacc | slots | mcslot | mcred forces a scheme (multicast ones fall back without an alias).
+static int choose_xmode(bool have_mc) {
+  const char *xm = getenv("TSGPU_XCHG");
+  if (xm && (!strcmp(xm, "slots") || !strcmp(xm, "ipc"))) return XMODE_SLOTS;
+  if (xm && !strcmp(xm, "mcslot")) return have_mc ? XMODE_MCSLOT : XMODE_SLOTS;
+  if (xm && !strcmp(xm, "mcred")) return have_mc ? XMODE_MCRED : XMODE_GACC;
+  if (xm && !strcmp(xm, "gacc")) return XMODE_GACC;
+  return have_mc ? XMODE_MCACC : XMODE_GACC;
+}
+
 // Move the engine's exchange state into rank_ptrs[rank] (one buffer per rank, all reachable from this
 // device) and pick the exchange mode.  The caller guarantees that no rank steps before all have attached.
 static int attach_symmetric(ts_engine *e, void *const *rank_ptrs, void *mc, unsigned long long total_ctas) {
@@ -572,13 +586,7 @@ static int attach_symmetric(ts_engine *e, void *const *rank_ptrs, void *mc, unsi
     e->prm.pst_peer[r] = &((Xchg *)rank_ptrs[r])->ps;
   }
   e->mc_arrivals = total_ctas;
-  // TSGPU_XCHG = slots | mcslot | mcred.  Measured on 2 B200s (profiles/r2_summary.md): peer stores 59.5-59.8 us
-  // per SVI iteration, one multicast store 60.5, in-switch multimem.red from every CTA 64.3 (148 x ranks
-  // atomics per word and GPU): the default stays the peer-store exchange, NVLS is opt-in.
-  const char *xm = getenv("TSGPU_XCHG");
-  int mode = XMODE_SLOTS;
-  if (xm && !strcmp(xm, "mcslot") && mc) mode = XMODE_MCSLOT;
-  else if (xm && !strcmp(xm, "mcred") && mc) mode = XMODE_MCRED;
+  int mode = choose_xmode(mc != nullptr);
   if (mode == XMODE_MCRED && total_ctas >= (1ull << (64 - tsfx::MC_CNT_SHIFT))) mode = XMODE_MCSLOT;  // arrival counter too narrow
   e->xmode = mode;
   fill_params(e);
@@ -902,7 +910,7 @@ int ts_load_bed_fanout(ts_engine **engines, int n, uint64_t loc_begin, uint64_t 
       std::vector<std::thread> th;
       for (unsigned t = 0; t < nthreads; ++t)
         th.emplace_back([&, t] {
-          for (uint64_t r = t; r < m; r += nthreads) memcpy(stage[b] + r * spitch, rows + (loc_begin + lo + r) * row_pitch, full_bytes);
+          for (uint64_t r = t; r < m; r += nthreads) memcpy(stage[b] + r * spitch, rows + (lo + r) * row_pitch, full_bytes);
         });
       for (auto &x : th) x.join();
     }
@@ -1257,6 +1265,8 @@ int ts_comm_connect(ts_engine *e, const void *all_handles) {
     e->prm.xpeer[r] = &((Xchg *)p)->x;
     e->prm.pst_peer[r] = &((Xchg *)p)->ps;
   }
+  e->xmode = choose_xmode(false);
+  fill_params(e);
   return TS_OK;
 }
 
@@ -1280,15 +1290,18 @@ int ts_comm_connect_local(ts_engine **engines, int n) {
       e->prm.xpeer[j] = engines[j]->xbuf;
       e->prm.pst_peer[j] = &engines[j]->xchg->ps;
     }
+    e->xmode = choose_xmode(false);
+    fill_params(e);
   }
-  // Opt-in (TSGPU_XCHG=mcslot|mcred, distinct devices): move the exchange state into symmetric buffers
-  // with an NVLS multicast alias when the fabric offers one.  Default: the peer-store exchange above.
+  // Distinct devices: move the exchange state into symmetric buffers with an NVLS multicast alias when the
+  // fabric offers one (one multimem.red per word instead of one red.add per peer); TSGPU_XCHG=gacc|slots|ipc
+  // keep the plain peer mappings set up above.
   bool distinct = n > 1;
   for (int i = 0; i < n; ++i)
     for (int j = 0; j < i; ++j)
       if (engines[i]->cfg.device == engines[j]->cfg.device) distinct = false;
   const char *xm = getenv("TSGPU_XCHG");
-  if (distinct && xm && (!strcmp(xm, "mcslot") || !strcmp(xm, "mcred")) && !engines[0]->symm) {
+  if (distinct && !(xm && (!strcmp(xm, "gacc") || !strcmp(xm, "slots") || !strcmp(xm, "ipc"))) && !engines[0]->symm) {
     std::vector<int> devs(n);
     for (int i = 0; i < n; ++i) devs[i] = engines[i]->cfg.device;
     std::string err;

@@ -102,6 +102,9 @@ __device__ __forceinline__ void ld_pair_sys(const unsigned long long *p, unsigne
 __device__ __forceinline__ void red_add(unsigned long long *p, unsigned long long v) {
   asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void red_add_sys(unsigned long long *p, unsigned long long v) {  // also into a peer's memory
+  asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 // NVLS (NVSwitch multicast): the operation is applied to every GPU's copy of the symmetric buffer.
 __device__ __forceinline__ void mm_red_add(unsigned long long *p, unsigned long long v) {
   asm volatile("multimem.red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -178,15 +181,14 @@ __host__ __device__ constexpr int persist_imax(int K) { return K <= 12 ? 4 : (K 
 __host__ __device__ constexpr int persist_itier(int K) { return K <= 12 ? TS_TIER_I : 1; }  // register tier of the TIER kernels
 constexpr int TIER_THREADS = 256;
 constexpr int TIER_JMAX = 16;  // codes of the shared-memory tier travel as 2 bits each in one register
-__host__ __device__ constexpr int persist_tmax(int K, int I) {
-#ifndef TS_I3_TMAX
-#define TS_I3_TMAX 256  // registers are allocated per 4 warps: 288 threads would cap at 168 registers like 384 do (spills)
-#endif
-  return K <= 12 ? (I == 1 ? 512 : (I == 2 ? 384 : (I == 3 ? TS_I3_TMAX : 256))) : (K <= 20 && I == 1 ? 384 : 256);
-}
+// 256 threads per CTA for every instantiation: the shard-sizing rule never gives a CTA more than eight
+// warps (two per scheduler), and at 256 threads ptxas may use 255 registers -- the 384- and 512-thread
+// caps of round 1 (168 / 128 registers) spilled 50-190 bytes in the I = 1 and I = 2 kernels.
+__host__ __device__ constexpr int persist_tmax(int, int) { return 256; }
 // shared memory without the E tier, for a kernel compiled for at most T threads per CTA (multiple of 16 bytes)
 __host__ __device__ constexpr size_t persist_smem_bytes(int K, int T) {
-  return (sizeof(double) * ((12 + 2 * RING) * K) + sizeof(long long) * (4 * K * (T / 32 + 1)) + 16 + sizeof(uint32_t) * RING + 15) / 16 * 16;
+  return (sizeof(double) * ((12 + 2 * RING) * K) + sizeof(long long) * (4 * K * (T / 32 + 1)) + 16 + sizeof(uint32_t) * RING +
+          sizeof(long long) * (8 * K) + 15) / 16 * 16;
 }
 // bytes of shared-memory E tier per individual-per-thread slot
 __host__ __device__ constexpr size_t persist_tier_slot_bytes(int K) { return sizeof(double) * K * TIER_THREADS; }
@@ -236,6 +238,7 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
   long long *s_fix = reinterpret_cast<long long *>(s_ring + RING * V);  // [NW][WS] per-warp fixed-point words
   int *s_flag = reinterpret_cast<int *>(s_fix + NW * WS);  // bit 0: round loop done, bit 1: abort
   uint32_t *s_ring_loc = reinterpret_cast<uint32_t *>(s_flag + 4);  // [RING]: locus of a ring slot, ~0 = empty
+  unsigned long long *s_lprev = reinterpret_cast<unsigned long long *>(s_ring_loc + RING);  // [2][NW] CTA 0, GACC modes: local totals so far
   double *s_E = reinterpret_cast<double *>(smem_raw + persist_smem_bytes(K, TM));  // TIER: [J][K][blockDim.x]
 
   PState *st = p.pst;
@@ -253,15 +256,25 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
   unsigned long long ph0[VPL], pl0[VPL], ph1[VPL], pl1[VPL];
   double lam[VPL];
   unsigned long long rc = st->round_ctr;
+  const bool gacc_mode = p.nranks > 1 && (p.xmode == XMODE_GACC || p.xmode == XMODE_MCACC);
   if (warp == 0) {
 #pragma unroll
     for (int q = 0; q < VPL; ++q) {
       const int v = lane + 32 * q;
       const bool act = v < V;
-      ph0[q] = act ? st->prev[0][v] : 0;
-      pl0[q] = act ? st->prev[0][V + v] : 0;
-      ph1[q] = act ? st->prev[1][v] : 0;
-      pl1[q] = act ? st->prev[1][V + v] : 0;
+      // the totals this lane has seen so far on the words it polls: the GPUs' accumulators in the GACC
+      // modes (CTA 0 keeps the local words' totals in shared memory then), the local words otherwise
+      const unsigned long long(*pv)[4 * MAXK] = gacc_mode ? st->gprev : st->prev;
+      ph0[q] = act ? pv[0][v] : 0;
+      pl0[q] = act ? pv[0][V + v] : 0;
+      ph1[q] = act ? pv[1][v] : 0;
+      pl1[q] = act ? pv[1][V + v] : 0;
+      if (gacc_mode && blockIdx.x == 0 && act) {
+        s_lprev[v] = st->prev[0][v];
+        s_lprev[V + v] = st->prev[0][V + v];
+        s_lprev[NW + v] = st->prev[1][v];
+        s_lprev[NW + V + v] = st->prev[1][V + v];
+      }
       lam[q] = 1024.0;  // idle lanes hold a large dummy so they never take f's small-argument path
     }
   }
@@ -591,7 +604,54 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
             // single GPU: every CTA waits for the local words.  Several GPUs: only CTA 0 does (it
             // forwards the GPU's totals); the other CTAs wait for the rank slots alone, which keeps
             // the pollers off the words the arrivals are being added to.
-            if (p.xmode == XMODE_MCRED) {
+            if (gacc_mode) {
+              if (blockIdx.x == 0) {  // this GPU's totals (local words complete) -> every rank's accumulator
+                const unsigned long long bh = s_lprev[par * NW + v], bl = s_lprev[par * NW + V + v];
+                while (true) {
+                  bool complete = false;
+                  for (int t = 0; t < POLL_BURST; ++t) {
+                    dh = ld_relaxed(&st->acc[par][v][0]) - bh;
+                    dl = ld_relaxed(&st->acc[par][V + v][0]) - bl;
+                    if ((dh >> FX_CNT_SHIFT) == G && (dl >> FX_CNT_SHIFT) == G) { complete = true; break; }
+                  }
+                  if (complete) break;
+                  if (guard.expired(p.timeout_ns)) { abort = true; break; }
+                }
+                s_lprev[par * NW + v] = bh + dh;
+                s_lprev[par * NW + V + v] = bl + dl;
+                dh &= FX_MASK;
+                dl &= FX_MASK;
+                tsfx::fold(dh, dl);  // low word below 2^44 again: the sum over the ranks stays inside the data bits
+                if (q == 0) TS_TRACE(82 + 2 * x);  // local words complete
+                const unsigned long long one = 1ull << FX_CNT_SHIFT;
+                if (p.xmode == XMODE_MCACC) {
+                  mm_red_add(&p.pst_mc->gacc[par][v][0], one + dh);
+                  mm_red_add(&p.pst_mc->gacc[par][V + v][0], one + dl);
+                } else {
+                  for (int r = 0; r < p.nranks; ++r) {
+                    red_add_sys(&p.pst_peer[r]->gacc[par][v][0], one + dh);
+                    red_add_sys(&p.pst_peer[r]->gacc[par][V + v][0], one + dl);
+                  }
+                }
+                if (q == 0) TS_TRACE(83 + 2 * x);  // forwarded
+              }
+              // every CTA: one word pair per statistic, complete when every rank has added its totals
+              const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q], want = (unsigned long long)p.nranks;
+              while (true) {
+                bool complete = false;
+                for (int t = 0; t < POLL_BURST; ++t) {
+                  dh = ld_relaxed_sys(&st->gacc[par][v][0]) - bh;
+                  dl = ld_relaxed_sys(&st->gacc[par][V + v][0]) - bl;
+                  if ((dh >> FX_CNT_SHIFT) == want && (dl >> FX_CNT_SHIFT) == want) { complete = true; break; }
+                }
+                if (complete) break;
+                if (guard.expired(p.timeout_ns)) { abort = true; break; }
+              }
+              if (par) { ph1[q] = bh + dh; pl1[q] = bl + dl; } else { ph0[q] = bh + dh; pl0[q] = bl + dl; }
+              dh &= FX_MASK;
+              dl &= FX_MASK;
+              tsfx::fold(dh, dl);
+            } else if (p.xmode == XMODE_MCRED) {
               // every CTA of every rank arrived on this GPU's copy: the single-GPU wait with a wider
               // count (ranks x CTAs) and the packed low word
               const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q];
@@ -626,7 +686,7 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
               dl &= FX_MASK;
               if (q == 0) TS_TRACE(82 + 2 * x);  // local words complete
             }
-            if (p.nranks > 1 && p.xmode != XMODE_MCRED) {
+            if (p.nranks > 1 && !gacc_mode && p.xmode != XMODE_MCRED) {
               const unsigned long long tag = ((rc + 1) & 1023ull) << FX_CNT_SHIFT;
               if (blockIdx.x == 0) {
                 if (p.xmode == XMODE_MCSLOT) mm_st_pair(&p.pst_mc->slot[p.rank][par][v][0], tag | dh, tag | dl);  // one store, the switch replicates it
@@ -740,10 +800,17 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
     for (int q = 0; q < VPL; ++q) {
       const int v = lane + 32 * q;
       if (v < V) {
-        st->prev[0][v] = ph0[q];
-        st->prev[0][V + v] = pl0[q];
-        st->prev[1][v] = ph1[q];
-        st->prev[1][V + v] = pl1[q];
+        unsigned long long(*pv)[4 * MAXK] = gacc_mode ? st->gprev : st->prev;
+        pv[0][v] = ph0[q];
+        pv[0][V + v] = pl0[q];
+        pv[1][v] = ph1[q];
+        pv[1][V + v] = pl1[q];
+        if (gacc_mode) {
+          st->prev[0][v] = s_lprev[v];
+          st->prev[0][V + v] = s_lprev[V + v];
+          st->prev[1][v] = s_lprev[NW + v];
+          st->prev[1][V + v] = s_lprev[NW + V + v];
+        }
       }
     }
     if (lane == 0) st->round_ctr = rc;

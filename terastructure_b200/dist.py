@@ -10,16 +10,23 @@ from . import capi
 
 _keepalive = []  # symmetric buffers must outlive the engines that use them
 
+MODES = {0: "CTA 0 stores the GPU totals into its slot on every peer, every CTA polls the rank slots",
+         1: "NVLS multicast store of the GPU totals (multimem.st), slots polled locally",
+         2: "NVLS in-switch reduction: multimem.red.add.u64 from every CTA of every GPU",
+         3: "CTA 0 adds the GPU totals into an accumulator on every rank (NVLink red.add.u64), every CTA polls one local word pair",
+         4: "CTA 0 adds the GPU totals with one multimem.red.add.u64 per word (NVLS), every CTA polls one local word pair"}
+
 
 def connect(engine, group=None):
     """Connect `engine` (rank, nranks as created) with its peers in `group` (default: WORLD).
 
-    Default: CUDA-IPC handles of the engines' own exchange buffers and peer stores over NVLink
-    (ts_comm_export / ts_comm_connect) -- the fastest scheme measured (profiles/r2_summary.md).
-    TSGPU_XCHG=slots|mcslot|mcred: a torch symmetric-memory buffer, optionally with its NVLS multicast
-    alias (ts_comm_attach_symmetric): one multicast store of the GPU totals, or the in-switch reduction
-    with multimem.red from every CTA.  Returns a dict describing what was set up; ends with a barrier,
-    so ts_steps may follow immediately."""
+    Default: a torch symmetric-memory buffer with its NVLS multicast alias (ts_comm_attach_symmetric): CTA 0
+    of every GPU adds the GPU's totals into an accumulator on every rank with ONE multimem.red per word and
+    every CTA polls one local word pair (XMODE_MCACC, the fastest scheme measured: profiles/r2_summary.md).
+    Without symmetric memory / NVLS, or with TSGPU_XCHG=gacc|slots|ipc: CUDA-IPC handles of the engines' own
+    buffers (ts_comm_export / ts_comm_connect) and one NVLink red.add per peer (XMODE_GACC), or the round-1
+    slot exchange (slots).  Returns a dict describing what was set up; ends with a barrier, so ts_steps may
+    follow immediately."""
     import torch
     import torch.distributed as dist
     group = group or dist.group.WORLD
@@ -28,7 +35,7 @@ def connect(engine, group=None):
     if world == 1:
         return info
     want = os.environ.get("TSGPU_XCHG", "")
-    if want in ("slots", "mcslot", "mcred"):
+    if want not in ("gacc", "slots", "ipc"):
         import torch.distributed._symmetric_memory as symm_mem
         dev = torch.device("cuda", int(engine.cfg.device))
         nbytes = int(capi.lib().ts_comm_state_bytes())
@@ -55,17 +62,15 @@ def connect(engine, group=None):
             _keepalive.append((buf, hdl))
             torch.cuda.synchronize(dev)
             dist.barrier(group)
-            mode = engine.comm_mode
-            return {"exchange": {0: "peer stores into symmetric-memory slots (CTA 0 forwards the GPU totals)",
-                                 1: "NVLS multicast store of the GPU totals (multimem.st), slots polled locally",
-                                 2: "NVLS in-switch reduction: multimem.red.add.u64 from every CTA of every GPU"}[mode],
-                    "mode": mode, "multicast": bool(mc), "detail": "torch symmetric memory"}
+            return {"exchange": MODES[engine.comm_mode], "mode": engine.comm_mode, "multicast": bool(mc),
+                    "detail": "torch symmetric memory"}
         info["detail"] = "symmetric memory unavailable (%s); " % why
     handles = [None] * world
     dist.all_gather_object(handles, engine.comm_export(), group=group)
     engine.comm_connect(handles)
     dist.barrier(group)
-    info["exchange"] = "peer stores into CUDA-IPC slots (CTA 0 forwards the GPU totals)"
-    info["mode"] = 0
+    info["exchange"] = MODES[engine.comm_mode]
+    info["mode"] = engine.comm_mode
     info["multicast"] = False
+    info["detail"] += "CUDA-IPC peer mappings"
     return info

@@ -2,8 +2,8 @@
 # round 2, GPU call 8 (eight B200s): exchange schemes in isolation at 8 ranks, bench at 8 GPUs for the
 # peer-store and the NVLS multicast-store exchange, then the full default line (1M x 1M, convergence run)
 mkdir -p gpurun_out
-O=gpurun_out/r2c8
-timeout 180 tools/dev/ubench_xchg 8 1000 > ${O}_xchg8.txt 2>&1; cat ${O}_xchg8.txt
+O=gpurun_out/r2c10
+echo skip ubench
 run() {  # $1 = tag, $2 = TSGPU_XCHG, rest = bench args
   tag=$1; m=$2; shift 2
   TSGPU_XCHG=$m TSGPU_TIMEOUT_S=30 timeout 840 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 \
@@ -19,8 +19,8 @@ except Exception as ex:
     print("$tag: FAILED", ex); print(open("${O}_bench_$tag.err").read()[-1500:])
 P
 }
-run ipc_short ipc --snps 50000 --steps 5 --warmup 3 --no-extras
-run mcslot_short mcslot --snps 50000 --steps 5 --warmup 3 --no-extras
-run full ipc --steps 10 --warmup 3
-TSGPU_XCHG=ipc TSGPU_TIMEOUT_S=30 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 tools/dev/trace_mp.py > ${O}_trace.log 2>&1
-cat gpurun_out/trace_mp_8_ipc.txt
+run gacc_short gacc --snps 50000 --steps 5 --warmup 3 --no-extras
+run mcacc_short mcacc --snps 50000 --steps 5 --warmup 3 --no-extras
+run full auto --steps 10 --warmup 3
+TSGPU_TIMEOUT_S=30 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 tools/dev/trace_mp.py > ${O}_trace.log 2>&1
+cat gpurun_out/trace_mp_8_default.txt
