@@ -1,0 +1,19 @@
+#!/bin/bash
+# round 2, GPU call 11 (one B200): final verification -- smoke, full GPU suite, the driver's bench commands
+# (ours and the reference arm), ncu launch list and --set full captures of the benchmarked instantiations
+mkdir -p gpurun_out
+O=gpurun_out/r2c11
+( time python -c "import __graft_entry__ as g; g.smoke()" ) > ${O}_smoke.log 2>&1; tail -3 ${O}_smoke.log
+( time timeout 1500 python -m pytest tests -m gpu -q ) > ${O}_tests.log 2>&1; tail -4 ${O}_tests.log
+( time timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 ) > ${O}_bench_1gpu.json 2> ${O}_bench_1gpu.err; tail -c 2500 ${O}_bench_1gpu.json; tail -3 ${O}_bench_1gpu.err
+( time timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 ) > ${O}_bench_ref.json 2> ${O}_bench_ref.err; tail -c 1800 ${O}_bench_ref.json; tail -3 ${O}_bench_ref.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file ${O}_launches.csv \
+   python bench.py --steps 2 --warmup 3 --batch 50 --snps 50000 --no-extras --no-cpu-baseline > ${O}_ncu_launch.log 2>&1
+for n in 100000 125000; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_persist -s 3 -c 1 -f -o ${O}_prof_n$n \
+     python bench.py --individuals $n --steps 1 --warmup 3 --batch 50 --snps 50000 --no-extras --no-cpu-baseline > ${O}_ncu_full_$n.log 2>&1
+  tail -1 ${O}_ncu_full_$n.log
+done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_persist -s 3 -c 1 -f -o ${O}_prof_n400000 \
+   python bench.py --individuals 400000 --steps 1 --warmup 3 --batch 20 --snps 20000 --no-extras --no-cpu-baseline > ${O}_ncu_full_400000.log 2>&1
+tail -1 ${O}_ncu_full_400000.log
