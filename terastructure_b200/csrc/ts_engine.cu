@@ -454,7 +454,7 @@ struct ts_engine {
   Xchg *xchg_own = nullptr;  // cudaMalloc'ed at creation (exported through CUDA IPC)
   Xchg *xchg_mc = nullptr;   // NVLS multicast alias of the symmetric buffer, or null
   Xbuf *xbuf = nullptr;      // &xchg->x
-  int xmode = XMODE_SLOTS;
+  int xmode = XMODE_GACC;
   unsigned long long mc_arrivals = 0;
   SymmGroup *symm = nullptr; // owned by rank 0's engine of a ts_comm_connect_local group
   bool staged = false;   // TSGPU_PATH=staged: one launch per round (debug cross-check path)
@@ -483,6 +483,9 @@ static cudaError_t dalloc(T **p, size_t count) {
 
 static int use_device(ts_engine *e) {
   CK(cudaSetDevice(e->cfg.device));
+  // a stale non-sticky error of an earlier runtime call in this thread (ours, e.g. from a refused ts_create's
+  // clean-up, or the host application's) must not be reported by the cudaGetLastError() after our next launch
+  (void)cudaGetLastError();
   return TS_OK;
 }
 
@@ -556,17 +559,17 @@ static cudaError_t launch_persist(ts_engine *e, uint32_t n_items) {
   return ts_launch_persist(e->K, e->ind_per_thread, e->tier, e->prm, n_items, e->grid_persist, e->block_persist, e->stream);
 }
 
-// How the ranks' totals of a round are exchanged (XMODE_*, ts_device.cuh; measurements in profiles/r2_summary.md:
-// 8 B200s in isolation, cycles per round: slots 8 332, one multimem.st 8 591, replicated accumulator with unicast
-// red.add 5 280 / with one multimem.red 4 947, multimem.red from every CTA 18 673; in the product on 2 B200s, us per
-// SVI iteration: slots 60.1, gacc 51.2, mcacc 48.9).  Default: mcacc where an NVLS alias exists, gacc otherwise.
-// TSGPU_XCHG = gacc | mcacc | slots | mcslot | mcred forces a scheme (multicast ones fall back without an alias).
+// How the ranks' totals of a round are exchanged (XMODE_*, ts_device.cuh): CTA 0 of every GPU adds the GPU's totals
+// into an accumulator replicated on every rank -- with one multimem.red per word where an NVLS alias exists
+// (XMODE_MCACC), with one NVLink red.add per peer and word otherwise (XMODE_GACC) -- and every CTA polls one local
+// word pair.  Measured against the alternatives on 8 B200s (profiles/r2_summary.md section 4; cycles per round in
+// isolation): slots written by every GPU and polled by every CTA 8 332, the same with one multimem.st 8 591,
+// multimem.red from every CTA 18 673, this scheme 5 280 (unicast) / 4 947 (multicast); in the product on 2 B200s,
+// us per SVI iteration: slots 60.1, gacc 51.2, mcacc 48.9.  The rejected schemes are no longer compiled in.
+// TSGPU_XCHG = gacc forces the unicast form (mcacc, or nothing: multicast when available).
 static int choose_xmode(bool have_mc) {
   const char *xm = getenv("TSGPU_XCHG");
-  if (xm && (!strcmp(xm, "slots") || !strcmp(xm, "ipc"))) return XMODE_SLOTS;
-  if (xm && !strcmp(xm, "mcslot")) return have_mc ? XMODE_MCSLOT : XMODE_SLOTS;
-  if (xm && !strcmp(xm, "mcred")) return have_mc ? XMODE_MCRED : XMODE_GACC;
-  if (xm && !strcmp(xm, "gacc")) return XMODE_GACC;
+  if (xm && (!strcmp(xm, "gacc") || !strcmp(xm, "slots") || !strcmp(xm, "ipc"))) return XMODE_GACC;
   return have_mc ? XMODE_MCACC : XMODE_GACC;
 }
 
@@ -586,9 +589,7 @@ static int attach_symmetric(ts_engine *e, void *const *rank_ptrs, void *mc, unsi
     e->prm.pst_peer[r] = &((Xchg *)rank_ptrs[r])->ps;
   }
   e->mc_arrivals = total_ctas;
-  int mode = choose_xmode(mc != nullptr);
-  if (mode == XMODE_MCRED && total_ctas >= (1ull << (64 - tsfx::MC_CNT_SHIFT))) mode = XMODE_MCSLOT;  // arrival counter too narrow
-  e->xmode = mode;
+  e->xmode = choose_xmode(mc != nullptr);
   fill_params(e);
   return TS_OK;
 }
@@ -850,6 +851,7 @@ int ts_destroy(ts_engine *e) {
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
+  (void)cudaGetLastError();  // freeing what a partly built engine never allocated leaves an error behind
   delete e;
   return TS_OK;
 }

@@ -32,6 +32,7 @@
 
 #include "ts_expsi.cuh"
 #include "ts_fixed.cuh"
+#include "ts_ftab.cuh"
 
 // Build-time switch for measurements (make lib SUFFIX=_nofence OPTS=8): bit 3 drops the fences of the
 // row hand-off (see "row hand-off" below) to price them.  Variants measured and rejected in round 2
@@ -87,18 +88,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// 16-byte (hi, lo) pair in one access: lanes of a warp touch consecutive pairs, so a GPU's totals
-// travel to a peer as a handful of 128-byte packets.  Each word carries its own tag, so a torn pair
-// is harmless.
-__device__ __forceinline__ void st_pair_sys(unsigned long long *p, unsigned long long a, unsigned long long b) {
-  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
-}
-__device__ __forceinline__ void ld_pair_sys(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
-  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-}
 __device__ __forceinline__ void red_add(unsigned long long *p, unsigned long long v) {
   asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -108,12 +97,6 @@ __device__ __forceinline__ void red_add_sys(unsigned long long *p, unsigned long
 // NVLS (NVSwitch multicast): the operation is applied to every GPU's copy of the symmetric buffer.
 __device__ __forceinline__ void mm_red_add(unsigned long long *p, unsigned long long v) {
   asm volatile("multimem.red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// 16-byte multicast store of a (hi, lo) pair; multimem.st has no .v2.u64 form, the bits travel as 4 x b32
-__device__ __forceinline__ void mm_st_pair(unsigned long long *p, unsigned long long a, unsigned long long b) {
-  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)a),
-               "r"((unsigned)(a >> 32)), "r"((unsigned)b), "r"((unsigned)(b >> 32))
-               : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -153,12 +136,19 @@ struct SpinGuard {
   }
 };
 
-// Optional phase trace (TSGPU_TRACE=1): CTA 0 / thread 0 stamps clock64() at phase boundaries.
+// Phase trace for developers: CTA 0 / thread 0 stamps clock64() at phase boundaries.  Compiled in only with
+// -DTS_TRACE_BUILD (make trace -> lib/libtsgpu_trace.so, used by tools/dev/trace_*.py with TSGPU_TRACE=1): in
+// the product every stamp would put a constant load, a compare and a branch on the round's dependent chain
+// (ncu showed the control warp waiting on exactly those between its FP64 instructions).
+#ifdef TS_TRACE_BUILD
 #define TS_TRACE(slot)                                                                        \
   do {                                                                                        \
     if (p.trace && blockIdx.x == 0 && tid == 0 && i < 64 && (unsigned)(slot) < 128u)          \
       p.trace[(size_t)i * 128 + (slot)] = clock64();                                          \
   } while (0)
+#else
+#define TS_TRACE(slot) do { } while (0)
+#endif
 
 // Row hand-off inside a launch.  The converged lambda row of a locus is needed again when the locus
 // is revisited (round-0 b, the convergence test's old lambda).  Every CTA forms that row itself, so
@@ -185,11 +175,13 @@ constexpr int TIER_JMAX = 16;  // codes of the shared-memory tier travel as 2 bi
 // warps (two per scheduler), and at 256 threads ptxas may use 255 registers -- the 384- and 512-thread
 // caps of round 1 (168 / 128 registers) spilled 50-190 bytes in the I = 1 and I = 2 kernels.
 __host__ __device__ constexpr int persist_tmax(int, int) { return 256; }
-// shared memory without the E tier, for a kernel compiled for at most T threads per CTA (multiple of 16 bytes)
-__host__ __device__ constexpr size_t persist_smem_bytes(int K, int T) {
+// shared memory without the E tier, for a kernel compiled for at most T threads per CTA (multiple of 16 bytes):
+// the round's working set, then the control path's coefficient table (ts_ftab.cuh)
+__host__ __device__ constexpr size_t persist_smem_work_bytes(int K, int T) {
   return (sizeof(double) * ((12 + 2 * RING) * K) + sizeof(long long) * (4 * K * (T / 32 + 1)) + 16 + sizeof(uint32_t) * RING +
           sizeof(long long) * (8 * K) + 15) / 16 * 16;
 }
+__host__ __device__ constexpr size_t persist_smem_bytes(int K, int T) { return persist_smem_work_bytes(K, T) + FTAB_BYTES; }
 // bytes of shared-memory E tier per individual-per-thread slot
 __host__ __device__ constexpr size_t persist_tier_slot_bytes(int K) { return sizeof(double) * K * TIER_THREADS; }
 
@@ -221,7 +213,10 @@ __device__ __forceinline__ void dot_b(const double (&en)[K], const double *b, do
   }
 }
 
-template <int K, int I, bool TIER>
+// MG = false: the single-GPU kernel, with no trace of the exchange code (a third of the round loop's instructions
+// and half of its branches; the control warp's path through a round is short enough to stay in the
+// instruction cache).  MG = true: several ranks, exchange chosen at run time by Params::xmode.
+template <int K, int I, bool TIER, bool MG>
 __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k_persist(Params p, uint32_t n_items) {
   static_assert(I >= 1, "the register tier holds at least one individual per thread");
   constexpr int V = 2 * K;
@@ -239,14 +234,22 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
   int *s_flag = reinterpret_cast<int *>(s_fix + NW * WS);  // bit 0: round loop done, bit 1: abort
   uint32_t *s_ring_loc = reinterpret_cast<uint32_t *>(s_flag + 4);  // [RING]: locus of a ring slot, ~0 = empty
   unsigned long long *s_lprev = reinterpret_cast<unsigned long long *>(s_ring_loc + RING);  // [2][NW] CTA 0, GACC modes: local totals so far
+  double *s_tab = reinterpret_cast<double *>(smem_raw + persist_smem_work_bytes(K, TM));  // [FTAB_NI][FTAB_STRIDE]: f and 1/f
   double *s_E = reinterpret_cast<double *>(smem_raw + persist_smem_bytes(K, TM));  // TIER: [J][K][blockDim.x]
 
   PState *st = p.pst;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
   const uint32_t GT = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
   const unsigned long long G = gridDim.x;
+  // Totals -> lambda (tsfx::to_double_plus): the four constants stay in registers for the whole launch.  Left to
+  // itself the compiler rebuilds them from the kernel parameters in every round (three constant-bank loads and an
+  // FP64 instruction in front of the round's first dependent DFMA); the empty asm makes them opaque.
   const tsfx::Unscale fxu = tsfx::unscale(p.fx_inv);
-  const double big_thr = 2.0 * V * p.thresh;  // one |delta lambda| this large rules convergence out
+  double fx_hi_inv = fxu.hi_inv, fx_lo_inv = fxu.lo_inv, fx_lo_off = fxu.lo_off;
+  double fx_hi_off_eta = fxu.hi_off + ((threadIdx.x & 1) ? p.eta1 : p.eta0);  // statistic v = lane + 32 q has the parity of the lane
+  asm volatile("" : "+d"(fx_hi_inv), "+d"(fx_lo_inv), "+d"(fx_lo_off), "+d"(fx_hi_off_eta));
+  // chg / V < thresh for certain below conv_lo, false for certain above conv_hi (see the convergence test)
+  const double conv_lo = (p.thresh * (double)V) * (1.0 - 0x1p-48), conv_hi = (p.thresh * (double)V) * (1.0 + 0x1p-48);
 
   // which statistics this lane ends up holding after tr_reduce
   int tr_start, tr_len;
@@ -256,7 +259,8 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
   unsigned long long ph0[VPL], pl0[VPL], ph1[VPL], pl1[VPL];
   double lam[VPL];
   unsigned long long rc = st->round_ctr;
-  const bool gacc_mode = p.nranks > 1 && (p.xmode == XMODE_GACC || p.xmode == XMODE_MCACC);
+  const int nranks = MG ? p.nranks : 1, xmode = MG ? p.xmode : XMODE_GACC;
+  constexpr bool gacc_mode = MG;  // several ranks: the replicated accumulator (XMODE_GACC / XMODE_MCACC) is the only exchange
   if (warp == 0) {
 #pragma unroll
     for (int q = 0; q < VPL; ++q) {
@@ -283,6 +287,31 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
   // slots of warps this CTA does not have stay zero, so the CTA sum below adds all WS - 1 slots
   // unconditionally (straight-line vector loads instead of a predicated chain)
   for (int idx = tid; idx < NW * WS; idx += blockDim.x) s_fix[idx] = 0;
+  for (int idx = tid; idx < FTAB_DOUBLES / 2; idx += blockDim.x)
+    reinterpret_cast<double2 *>(s_tab)[idx] = reinterpret_cast<const double2 *>(d_ftab)[idx];
+  // b = f(lambda_t) / f(lambda_0 + lambda_1) (estimate_beta, cc:279-296) for the statistic of each lane of a whole
+  // warp: table-driven while every lane's arguments lie in the table's domain (ts_ftab.cuh)
+  const uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(s_tab);  // the table's address in the shared window
+  // whole warp: lane's statistic(s) own[q] of a lambda row -> b; the table serves the row only if ALL its 2K
+  // statistics (and their pair sums) lie in the table's domain, so that every path that turns a given row into b
+  // (helper warp, control warp at a launch's first SNP, control warp between rounds) takes the same branch
+  auto beta_row = [&](const double (&own)[VPL], double (&b)[VPL]) {
+    double s2[VPL];
+    bool in_tab = true;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      const int v = lane + 32 * q;
+      const double other = __shfl_xor_sync(0xffffffffu, own[q], 1);
+      const double l0 = (v & 1) ? other : own[q], l1 = (v & 1) ? own[q] : other;
+      s2[q] = l0 + l1;  // the reference adds 0 + l0 + l1 (cc:283-286): 0 + l0 is exact
+      in_tab = in_tab && ftab_covers(own[q], s2[q]);
+    }
+    in_tab = __all_sync(0xffffffffu, in_tab);
+#pragma unroll
+    for (int q = 0; q < VPL; ++q)
+      b[q] = in_tab ? ftab_f_sh(tab_sa, ftab_index(own[q]), own[q]) * ftab_g_sh(tab_sa, ftab_index(s2[q]), s2[q])
+                    : f_expsi(own[q]) * fast_rcp(f_expsi(s2[q]));
+  };
 
   // this thread's individuals and their E = exp(psi(gamma)) rows: register tier
   constexpr int IR = I;
@@ -354,16 +383,13 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
       }
     };
     auto b_from_row = [&](uint32_t loc, double *dst, double *row_dst) {
-      double own[VPL];
+      double own[VPL], b[VPL];
       load_row(loc, own, true);
+      beta_row(own, b);
 #pragma unroll
       for (int q = 0; q < VPL; ++q) {
         const int v = lane + 32 * q;
-        const double other = __shfl_xor_sync(0xffffffffu, own[q], 1);
-        const double l0 = (v & 1) ? other : own[q], l1 = (v & 1) ? own[q] : other;
-        const double s = l0 + l1;  // the reference adds 0 + l0 + l1 (cc:283-286): 0 + l0 is exact
-        const double b = f_expsi(own[q]) * fast_rcp(f_expsi(s));
-        if (v < V) { dst[v] = b; row_dst[v] = own[q]; }
+        if (v < V) { dst[v] = b[q]; row_dst[v] = own[q]; }
       }
     };
     const bool can_prepare = p.max_rounds >= 2;
@@ -390,15 +416,11 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
         load_row(it.loc, lam, false);
       }
       if (!prepared) {
+        double b[VPL];
+        beta_row(lam, b);
 #pragma unroll
-        for (int q = 0; q < VPL; ++q) {
-          const int v = lane + 32 * q;
-          const double other = __shfl_xor_sync(0xffffffffu, lam[q], 1);
-          const double l0 = (v & 1) ? other : lam[q], l1 = (v & 1) ? lam[q] : other;
-          const double s = l0 + l1;  // the reference adds 0 + l0 + l1 (cc:283-286): 0 + l0 is exact
-          const double b = f_expsi(lam[q]) * fast_rcp(f_expsi(s));
-          if (v < V) b_first[v] = b;
-        }
+        for (int q = 0; q < VPL; ++q)
+          if (lane + 32 * q < V) b_first[lane + 32 * q] = b[q];
       }
       if (lane == 0) *s_flag = 0;
     }
@@ -563,13 +585,8 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
 #pragma unroll
         for (int ww = 0; ww < WS - 1; ++ww) { hi += sh[ww]; lo += sl[ww]; }
         tsfx::normalize(hi, lo);  // the low word becomes [0, 2^44)
-        if (p.xmode == XMODE_MCRED) {  // in-switch: one arrival per CTA on EVERY GPU's copy of the word
-          mm_red_add(&p.pst_mc->acc[par][v][0], (unsigned long long)hi + (1ull << tsfx::MC_CNT_SHIFT));
-          mm_red_add(&p.pst_mc->acc[par][V + v][0], ((unsigned long long)lo >> tsfx::MC_LO_DROP) + (1ull << tsfx::MC_CNT_SHIFT));
-        } else {
-          red_add(&st->acc[par][v][0], (unsigned long long)hi + (1ull << FX_CNT_SHIFT));
-          red_add(&st->acc[par][V + v][0], (unsigned long long)lo + (1ull << FX_CNT_SHIFT));
-        }
+        red_add(&st->acc[par][v][0], (unsigned long long)hi + (1ull << FX_CNT_SHIFT));
+        red_add(&st->acc[par][V + v][0], (unsigned long long)lo + (1ull << FX_CNT_SHIFT));
       }
       TS_TRACE(2 + 8 * x + 3);
       // Row hand-off, both sides off the critical path.  Writer: the lanes of CTA 0 that stored the rows of
@@ -601,9 +618,9 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
           unsigned long long dh = 0, dl = 0;
           if (v < V) {
             SpinGuard guard;
-            // single GPU: every CTA waits for the local words.  Several GPUs: only CTA 0 does (it
-            // forwards the GPU's totals); the other CTAs wait for the rank slots alone, which keeps
-            // the pollers off the words the arrivals are being added to.
+            // single GPU: every CTA waits for the local words.  Several GPUs: only CTA 0 does (it forwards
+            // the GPU's totals into every rank's accumulator); the other CTAs wait for the accumulator alone,
+            // which keeps the pollers off the words the arrivals are being added to.
             if (gacc_mode) {
               if (blockIdx.x == 0) {  // this GPU's totals (local words complete) -> every rank's accumulator
                 const unsigned long long bh = s_lprev[par * NW + v], bl = s_lprev[par * NW + V + v];
@@ -624,11 +641,11 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
                 tsfx::fold(dh, dl);  // low word below 2^44 again: the sum over the ranks stays inside the data bits
                 if (q == 0) TS_TRACE(82 + 2 * x);  // local words complete
                 const unsigned long long one = 1ull << FX_CNT_SHIFT;
-                if (p.xmode == XMODE_MCACC) {
+                if (xmode == XMODE_MCACC) {
                   mm_red_add(&p.pst_mc->gacc[par][v][0], one + dh);
                   mm_red_add(&p.pst_mc->gacc[par][V + v][0], one + dl);
                 } else {
-                  for (int r = 0; r < p.nranks; ++r) {
+                  for (int r = 0; r < nranks; ++r) {
                     red_add_sys(&p.pst_peer[r]->gacc[par][v][0], one + dh);
                     red_add_sys(&p.pst_peer[r]->gacc[par][V + v][0], one + dl);
                   }
@@ -636,7 +653,7 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
                 if (q == 0) TS_TRACE(83 + 2 * x);  // forwarded
               }
               // every CTA: one word pair per statistic, complete when every rank has added its totals
-              const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q], want = (unsigned long long)p.nranks;
+              const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q], want = (unsigned long long)nranks;
               while (true) {
                 bool complete = false;
                 for (int t = 0; t < POLL_BURST; ++t) {
@@ -651,25 +668,7 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
               dh &= FX_MASK;
               dl &= FX_MASK;
               tsfx::fold(dh, dl);
-            } else if (p.xmode == XMODE_MCRED) {
-              // every CTA of every rank arrived on this GPU's copy: the single-GPU wait with a wider
-              // count (ranks x CTAs) and the packed low word
-              const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q];
-              while (true) {
-                bool complete = false;
-                for (int t = 0; t < POLL_BURST; ++t) {
-                  dh = ld_relaxed_sys(&st->acc[par][v][0]) - bh;
-                  dl = ld_relaxed_sys(&st->acc[par][V + v][0]) - bl;
-                  if ((dh >> tsfx::MC_CNT_SHIFT) == p.mc_arrivals && (dl >> tsfx::MC_CNT_SHIFT) == p.mc_arrivals) { complete = true; break; }
-                }
-                if (complete) break;
-                if (guard.expired(p.timeout_ns)) { abort = true; break; }
-              }
-              if (par) { ph1[q] = bh + dh; pl1[q] = bl + dl; } else { ph0[q] = bh + dh; pl0[q] = bl + dl; }
-              dh &= tsfx::MC_MASK;
-              dl &= tsfx::MC_MASK;
-              tsfx::mc_unpack(dh, dl);
-            } else if (p.nranks == 1 || blockIdx.x == 0) {
+            } else {
               const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q];
               while (true) {
                 bool complete = false;
@@ -686,84 +685,62 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
               dl &= FX_MASK;
               if (q == 0) TS_TRACE(82 + 2 * x);  // local words complete
             }
-            if (p.nranks > 1 && !gacc_mode && p.xmode != XMODE_MCRED) {
-              const unsigned long long tag = ((rc + 1) & 1023ull) << FX_CNT_SHIFT;
-              if (blockIdx.x == 0) {
-                if (p.xmode == XMODE_MCSLOT) mm_st_pair(&p.pst_mc->slot[p.rank][par][v][0], tag | dh, tag | dl);  // one store, the switch replicates it
-                else for (int r = 0; r < p.nranks; ++r) st_pair_sys(&p.pst_peer[r]->slot[p.rank][par][v][0], tag | dh, tag | dl);
-                if (p.xflush) __threadfence_system();  // push the NVLink writes out now
-                if (q == 0) TS_TRACE(83 + 2 * x);  // peer stores issued
-              }
-              // all ranks' slots are read together (one round trip per sweep), stale ones re-read
-              unsigned long long th = 0, tl = 0;
-              for (int r0 = 0; r0 < p.nranks; r0 += 8) {
-                unsigned long long wh[8], wl[8];
-                unsigned pending = 0;
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                  if (r0 + u < p.nranks) pending |= 1u << u;
-                while (pending) {
-                  for (int t = 0; t < POLL_BURST && pending; ++t) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                      if (pending & (1u << u)) ld_pair_sys(&st->slot[r0 + u][par][v][0], wh[u], wl[u]);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                      if ((pending & (1u << u)) && (wh[u] & ~FX_MASK) == tag && (wl[u] & ~FX_MASK) == tag) pending &= ~(1u << u);
-                  }
-                  if (pending && guard.expired(p.timeout_ns)) { abort = true; break; }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                  if (r0 + u < p.nranks) { th += wh[u] & FX_MASK; tl += wl[u] & FX_MASK; }
-              }
-              dh = th;
-              dl = tl;
-              tsfx::fold(dh, dl);  // the ranks' low words can add up to 2^52 and more: carry first
-            }
           }
           // update_lambda (cc:267-277): lambda = eta + S, u64 -> double through the mantissa (both words < 2^52)
-          tot[q] = tsfx::to_double_plus(dh, dl, fxu, (v & 1) ? p.eta1 : p.eta0);
+          tot[q] = fma(tsfx::double_of((long long)(dh | 0x4330000000000000ull)), fx_hi_inv, fx_hi_off_eta) +
+                   fma(tsfx::double_of((long long)(dl | 0x4330000000000000ull)), fx_lo_inv, fx_lo_off);
         }
         TS_TRACE(2 + 8 * x + 4);
-        // new lambda -> new b first (the critical path of the round); convergence test afterwards
-        double own[VPL], oldlam[VPL];
+        // New lambda -> new b AND the convergence sum in ONE basic block: both are chains of dependent FP64
+        // operations (b: argument reduction, four Estrin levels, a product; the sum: five shuffle + DADD levels),
+        // a warp issues in order, and only instructions of one block can be interleaved by the compiler --
+        // written one after the other, behind the table-or-fallback branch, the two chains cost their sum
+        // (~650 cycles) instead of the longer one.
+        // Convergence (cc:359-365): mean |delta lambda| < thresh.  chg / V < thresh is decided without the IEEE
+        // division (eight more dependent instructions) whenever chg is further than 2^-48 (relative) from
+        // thresh * V -- the division's and the product's roundings move the boundary by at most 2^-52.
+        double own[VPL], oldlam[VPL], s2[VPL], dlt[VPL];
         double *bn = s_b + ((x + 1) & 1) * V;
+        const bool last = x + 1 >= p.max_rounds;
+        bool in_tab = true;
 #pragma unroll
         for (int q = 0; q < VPL; ++q) {
           const int v = lane + 32 * q;
           oldlam[q] = lam[q];
           own[q] = (v < V) ? tot[q] : 1024.0;  // idle lanes: any large value
           lam[q] = own[q];
-          if (x + 1 < p.max_rounds) {  // the last permitted round has no successor that would read b
-            const double fo = f_expsi(own[q]);
-            const double other = __shfl_xor_sync(0xffffffffu, own[q], 1);
-            const double l0 = (v & 1) ? other : own[q], l1 = (v & 1) ? own[q] : other;
-            const double s = l0 + l1;  // the reference adds 0 + l0 + l1 (cc:283-286): 0 + l0 is exact
-            const double b = fo * fast_rcp(f_expsi(s));  // estimate_beta (cc:279-296)
-            if (v < V) bn[v] = b;
-          }
+          const double other = __shfl_xor_sync(0xffffffffu, own[q], 1);
+          const double l0 = (v & 1) ? other : own[q], l1 = (v & 1) ? own[q] : other;
+          s2[q] = l0 + l1;  // the reference adds 0 + l0 + l1 (cc:283-286): 0 + l0 is exact
+          dlt[q] = (v < V) ? fabs(own[q] - oldlam[q]) : 0.0;
+          in_tab = in_tab && ftab_covers(own[q], s2[q]);
         }
-        // Convergence (cc:359-365): mean |delta lambda| < thresh.  The sum needs five dependent
-        // 64-bit shuffle levels and a division on the round's critical path, so it is only formed
-        // when it can matter: not in the last permitted round (done regardless), and not when one
-        // statistic alone moved by 2*V*thresh or more (the mean is then >= thresh whatever the
-        // rounding) -- both decided by one warp vote.
-        const bool last = x + 1 >= p.max_rounds;
-        bool big = false;
-#pragma unroll
-        for (int q = 0; q < VPL; ++q)
-          if (lane + 32 * q < V) big |= fabs(own[q] - oldlam[q]) >= big_thr;
-        big = __any_sync(0xffffffffu, big);
+        in_tab = __all_sync(0xffffffffu, in_tab);
         abort = __any_sync(0xffffffffu, abort);
-        bool done = last;
-        if (!last && !big) {
-          double chg = 0.0;
+        double chg = 0.0;
+        if (in_tab) {
 #pragma unroll
-          for (int q = 0; q < VPL; ++q)
-            if (lane + 32 * q < V) chg += fabs(own[q] - oldlam[q]);
+          for (int q = 0; q < VPL; ++q) {
+            const double b = ftab_f_sh(tab_sa, ftab_index(own[q]), own[q]) * ftab_g_sh(tab_sa, ftab_index(s2[q]), s2[q]);  // estimate_beta (cc:279-296)
+            if (lane + 32 * q < V && !last) bn[lane + 32 * q] = b;  // the last permitted round has no successor that would read b
+            chg += dlt[q];
+          }
           chg = warp_sum(chg);
-          done = chg / (double)V < p.thresh;
+        } else {
+#pragma unroll
+          for (int q = 0; q < VPL; ++q) {
+            const double b = f_expsi(own[q]) * fast_rcp(f_expsi(s2[q]));
+            if (lane + 32 * q < V && !last) bn[lane + 32 * q] = b;
+            chg += dlt[q];
+          }
+          chg = warp_sum(chg);
+        }
+        TS_TRACE(2 + 8 * x + 7);
+        bool done = last;
+        if (!last) {
+          if (chg < conv_lo) done = true;
+          else if (chg > conv_hi) done = false;
+          else done = chg / (double)V < p.thresh;
         }
         if (done && blockIdx.x == 0) {  // the finished row to global memory; every CTA keeps it in `lam` for its ring
 #pragma unroll

@@ -14,8 +14,8 @@
 #define TS_CAT(a, b) TS_CAT2(a, b)
 #define TS_RANGE_FN TS_CAT(ts_launch_persist_k, TS_KLO)
 
-template <int K, int I, bool TIER>
-static cudaError_t launch_ki(const Params &prm, uint32_t n_items, int grid, int block, cudaStream_t stream) {
+template <int K, int I, bool TIER, bool MG>
+static cudaError_t launch_kim(const Params &prm, uint32_t n_items, int grid, int block, cudaStream_t stream) {
   if constexpr (I > tsp::persist_imax(K) || (TIER && I != tsp::persist_itier(K))) {
     return cudaErrorInvalidValue;
   } else {
@@ -27,14 +27,20 @@ static cudaError_t launch_ki(const Params &prm, uint32_t n_items, int grid, int 
     int dev = 0;
     cudaGetDevice(&dev);
     if (smem > 48 * 1024 && attr_set[dev & 63] < smem) {
-      cudaError_t er = cudaFuncSetAttribute(tsp::k_persist<K, I, TIER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t er = cudaFuncSetAttribute(tsp::k_persist<K, I, TIER, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (er != cudaSuccess) return er;
       attr_set[dev & 63] = smem;
     }
     Params p = prm;
     void *args[] = {(void *)&p, (void *)&n_items};
-    return cudaLaunchCooperativeKernel((const void *)tsp::k_persist<K, I, TIER>, dim3(grid), dim3(block), args, smem, stream);
+    return cudaLaunchCooperativeKernel((const void *)tsp::k_persist<K, I, TIER, MG>, dim3(grid), dim3(block), args, smem, stream);
   }
+}
+
+template <int K, int I, bool TIER>
+static cudaError_t launch_ki(const Params &prm, uint32_t n_items, int grid, int block, cudaStream_t stream) {
+  return prm.nranks > 1 ? launch_kim<K, I, TIER, true>(prm, n_items, grid, block, stream)
+                        : launch_kim<K, I, TIER, false>(prm, n_items, grid, block, stream);
 }
 
 template <int K>

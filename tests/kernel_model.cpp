@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY (never linked into the product): a sequential host model of the
 // persistent kernel's ALGORITHM -- the reformulation that the CUDA code implements -- built from
-// the kernel's own host-compilable arithmetic (ts_expsi.cuh: f = exp o digamma, fast_rcp;
+// the kernel's own host-compilable arithmetic (ts_expsi.cuh: f = exp o digamma, fast_rcp; ts_ftab.cuh: the control path's f, 1/f;
 // ts_fixed.cuh: fixed-point words), so that the reformulation can be checked against the oracle
 // without a GPU:
 //   E = f(gamma) instead of Elogtheta; b = f(lambda_t) / f(lambda_0 + lambda_1) instead of Elogbeta;
@@ -14,8 +14,10 @@
 #include <cstdint>
 #include <vector>
 
+#define TS_FTAB_HOST_TABLE
 #include "ts_expsi.cuh"
 #include "ts_fixed.cuh"
+#include "ts_ftab.cuh"
 
 extern "C" int km_train(uint32_t n, uint32_t l, uint32_t k, const uint8_t *y /* [l][n]: 0,1,2; 3 = missing or held out */,
                         double *gamma /* [n][k] */, uint32_t *cnt /* [n] */, double *lambda /* [l][k][2] */,
@@ -28,13 +30,12 @@ extern "C" int km_train(uint32_t n, uint32_t l, uint32_t k, const uint8_t *y /* 
   std::vector<double> E((size_t)n * k), b(V), bn(V), lam(V), q0(n), q1(n), vv(V);
   for (size_t i = 0; i < (size_t)n * k; ++i) E[i] = tsp::f_expsi(gamma[i]);
   const uint32_t warp_span = 32u * (uint32_t)(ipt > 0 ? ipt : 1);
+  // estimate_beta as the control warp does it (ts_ftab.cuh): the table-driven f and 1/f while every statistic
+  // of the row (and every pair sum) lies in the table's domain, f_expsi / fast_rcp for the whole row otherwise
   auto b_from = [&](const double *row, double *dst) {
-    for (uint32_t kk = 0; kk < k; ++kk) {
-      const double s = row[2 * kk] + row[2 * kk + 1];
-      const double rs = tsp::fast_rcp(tsp::f_expsi(s));
-      dst[2 * kk] = tsp::f_expsi(row[2 * kk]) * rs;
-      dst[2 * kk + 1] = tsp::f_expsi(row[2 * kk + 1]) * rs;
-    }
+    bool all_in = true;
+    for (uint32_t v = 0; v < V; ++v) all_in = all_in && tsp::ftab_covers(row[v], row[v & ~1u] + row[v | 1u]);
+    for (uint32_t v = 0; v < V; ++v) dst[v] = tsp::beta_ratio(tsp::h_ftab, all_in, row[v], row[v & ~1u] + row[v | 1u]);
   };
   for (uint32_t it = 0; it < nlocs; ++it) {
     const uint32_t loc = locs[it];

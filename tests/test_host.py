@@ -241,7 +241,7 @@ def test_shard_plan_geometry():
     # beyond the register-resident capacity: 2 individuals per thread in registers, more in shared memory
     assert ts.plan_shard(400000, 10, sms) == (2, 148, 256) and ts.plan_tiers(400000, 10, sms) == (9, 0)
     j, streamed = ts.plan_tiers(1_000_000, 10, sms)
-    assert j == 11 and streamed == 1_000_000 - 13 * 148 * 256   # 227 KB of shared memory per CTA hold 11 more
+    assert j == 10 and streamed == 1_000_000 - 12 * 148 * 256   # 227 KB of shared memory per CTA: the control path's 20 KB table + 10 more
     assert ts.plan_tiers(100000, 10, sms) == (0, 0)
     for k in (1, 2, 6, 10, 12, 13, 16, 20, 21, 32):
         for n in (1, 3, 31, 33, 200, 4097, 9999, 37888, 37889, 56000, 75776, 99999, 113664, 113665, 151552, 151553, 10 ** 6):
@@ -292,6 +292,37 @@ def test_exp_digamma_host_model_vs_mpmath(tmp_path):
             assert e == 0.0
     assert worst["large"] < 5e-16 and worst["mid"] < 1e-14 and worst["small"] < 3e-13, worst
     assert worst["rcp"] < 2.3e-16 and worst["exp"] < 1e-14, worst
+
+
+def test_control_path_table_vs_mpmath(tmp_path):
+    """ts_ftab.cuh compiled for the host (the kernel's own source and coefficient table, tools/gen_ftab.py): the
+    piecewise polynomials for f = exp(digamma) and 1/f that the control warp turns a lambda row into b with
+    (estimate_beta, snpsamplinge.cc:279-296) against mpmath over the whole domain [1, 2^24), interval boundaries
+    included; arguments outside are refused (the kernel falls back to ts_expsi.cuh there); b = f(x) / f(s) through
+    either path agrees with mpmath."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    exe = str(tmp_path / "ftab_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "terastructure_b200", "csrc"),
+                    "-o", exe, os.path.join(ROOT, "tests", "ftab_check.cpp")], check=True)
+    out = subprocess.run([exe, "2400"], capture_output=True, text=True, check=True).stdout
+    wf = wg = wb = 0.0
+    n_in = 0
+    for line in out.splitlines():
+        x, inside, f, g, t, b = line.split()
+        x, inside = float.fromhex(x), int(inside)
+        assert inside == (1.0 <= x < 2.0 ** 24), x
+        X = mp.mpf(x)
+        F = mp.exp(mp.digamma(X))
+        B = F / mp.exp(mp.digamma(2 * X + mp.mpf("0.25")))
+        wb = max(wb, abs(float(mp.mpf(float.fromhex(b)) / B - 1)))
+        if not inside:
+            continue
+        n_in += 1
+        assert -1.0 <= float.fromhex(t) < 1.0
+        wf = max(wf, abs(float(mp.mpf(float.fromhex(f)) / F - 1)))
+        wg = max(wg, abs(float(mp.mpf(float.fromhex(g)) * F - 1)))
+    assert n_in > 2000 and wf < 6e-16 and wg < 8e-16 and wb < 2e-14, (n_in, wf, wg, wb)
 
 
 @pytest.mark.parametrize("n,l,seed", [(2500, 1800, 99), (150, 1200, 3)])

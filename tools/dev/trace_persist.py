@@ -1,6 +1,8 @@
 import os, sys
 import numpy as np
 os.environ["TSGPU_TRACE"] = "1"
+# the phase stamps are compiled into the developer library only (make -C terastructure_b200/csrc trace; K = 10)
+os.environ.setdefault("TSGPU_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "terastructure_b200", "lib", "libtsgpu_trace.so"))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import terastructure_b200 as ts
 from terastructure_b200 import synth
