@@ -189,6 +189,10 @@ __host__ __device__ constexpr size_t persist_tier_slot_bytes(int K) { return siz
 // dependent FMA chain per t (register tier: three individuals per thread give the FP64 pipe enough
 // independent chains).  SPLIT = true: two half-length chains per t for the shared-memory and streaming
 // tiers, whose individuals pass one or two at a time (dependent DFMA latency on B200: ~23 cycles).
+// b = f(own) / f(s) without the table (an argument outside its domain): out of line, so that the rarely taken
+// ~150 instructions do not sit between the table path and the end of the control block
+static __device__ __noinline__ double beta_analytic(double own, double s) { return f_expsi(own) * fast_rcp(f_expsi(s)); }
+
 template <int K, bool SPLIT>
 __device__ __forceinline__ void dot_b(const double (&en)[K], const double *b, double &s0, double &s1) {
   if constexpr (!SPLIT || K < 4) {
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
 #pragma unroll
     for (int q = 0; q < VPL; ++q)
       b[q] = in_tab ? ftab_f_sh(tab_sa, ftab_index(own[q]), own[q]) * ftab_g_sh(tab_sa, ftab_index(s2[q]), s2[q])
-                    : f_expsi(own[q]) * fast_rcp(f_expsi(s2[q]));
+                    : beta_analytic(own[q], s2[q]);
   };
 
   // this thread's individuals and their E = exp(psi(gamma)) rows: register tier
@@ -729,28 +733,20 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
         } else {
 #pragma unroll
           for (int q = 0; q < VPL; ++q) {
-            const double b = f_expsi(own[q]) * fast_rcp(f_expsi(s2[q]));
+            const double b = beta_analytic(own[q], s2[q]);
             if (lane + 32 * q < V && !last) bn[lane + 32 * q] = b;
             chg += dlt[q];
           }
           chg = warp_sum(chg);
         }
         TS_TRACE(2 + 8 * x + 7);
-        bool done = last;
-        if (!last) {
-          if (chg < conv_lo) done = true;
-          else if (chg > conv_hi) done = false;
-          else done = chg / (double)V < p.thresh;
-        }
-        if (done && blockIdx.x == 0) {  // the finished row to global memory; every CTA keeps it in `lam` for its ring
-#pragma unroll
-          for (int q = 0; q < VPL; ++q)
-            if (lane + 32 * q < V) st_row(p.lambda + (size_t)it.loc * V + lane + 32 * q, own[q]);
-        }
+        // (the finished row and the round count go to global memory after the loop: nothing but the decision and
+        // the flag stands between the totals and the barrier that releases the other warps)
+        bool done = last || chg < conv_lo;
+        if (!done && chg <= conv_hi) done = chg / (double)V < p.thresh;
         if (lane == 0) {
           if (abort) { st->fault = 1; *s_flag = 2; }
           else if (done) *s_flag = 1;
-          if (done && blockIdx.x == 0) p.rounds[i] = x + 1;
         }
         TS_TRACE(2 + 8 * x + 5);
       }
@@ -765,6 +761,12 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
 
     // early-converged SNPs take the gamma step here; the usual case (all rounds run) took it
     // inside the last round, in the shadow of that round's grid barrier
+    if (blockIdx.x == 0 && warp == 0) {  // the finished row (in `lam`; every CTA keeps it for its ring) to global memory
+#pragma unroll
+      for (int q = 0; q < VPL; ++q)
+        if (lane + 32 * q < V) st_row(p.lambda + (size_t)it.loc * V + lane + 32 * q, lam[q]);
+      if (lane == 0) p.rounds[i] = x;
+    }
     if (!next_prepared) prepare_next();  // the SNP ended after its first round
     if (!gamma_done && !(it.flags & ITEM_HOL)) gamma_step(x == 1 ? b_first : s_b + ((x - 1) & 1) * V);
     TS_TRACE(100);
