@@ -41,11 +41,24 @@
 #define TS_OPTS 0
 #endif
 #define TS_OPT_NOFENCE ((TS_OPTS) & 8)
+#ifndef TS_PAIR_WORDS   // 1: the two words of a statistic are adjacent and polled with one 16-byte load
+#define TS_PAIR_WORDS 1
+#endif
+#ifndef TS_CODE_AHEAD   // 1: the register tier's genotype bytes are loaded one SNP ahead
+#define TS_CODE_AHEAD 1
+#endif
 #ifndef TS_TIER_UNROLL  // individuals of the shared-memory / streaming tiers in flight per thread (K <= 12)
 #define TS_TIER_UNROLL 2
 #endif
 #ifndef TS_TIER_I       // individuals per thread in registers in the TIER kernels (K <= 12)
 #define TS_TIER_I 2
+#endif
+
+// address of the low word of statistic v in an accumulator array a[2][4 MAXK][128] (the high word is a[par][v][0])
+#if TS_PAIR_WORDS
+#define TS_LO(a, par, v) (&(a)[par][v][1])
+#else
+#define TS_LO(a, par, v) (&(a)[par][V + (v)][0])
 #endif
 
 namespace tsp {
@@ -87,6 +100,32 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
   unsigned long long v;
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+// 16-byte (hi, lo) pair in one access; each word carries its own arrival count, so a torn pair is harmless
+__device__ __forceinline__ void ld_pair(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void ld_pair_sys(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+// one poll of a statistic's two words
+__device__ __forceinline__ void poll_pair(const unsigned long long *ph, const unsigned long long *pl, unsigned long long &h, unsigned long long &l) {
+#if TS_PAIR_WORDS
+  (void)pl;
+  ld_pair(ph, h, l);
+#else
+  h = ld_relaxed(ph);
+  l = ld_relaxed(pl);
+#endif
+}
+__device__ __forceinline__ void poll_pair_sys(const unsigned long long *ph, const unsigned long long *pl, unsigned long long &h, unsigned long long &l) {
+#if TS_PAIR_WORDS
+  (void)pl;
+  ld_pair_sys(ph, h, l);
+#else
+  h = ld_relaxed_sys(ph);
+  l = ld_relaxed_sys(pl);
+#endif
 }
 __device__ __forceinline__ void red_add(unsigned long long *p, unsigned long long v) {
   asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -343,12 +382,32 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
   }
   __syncthreads();
 
+  // Genotype bytes of the register tier's individuals travel one SNP ahead: the loads for SNP i + 1 are issued at
+  // the start of SNP i and first touched at the start of SNP i + 1, so the dependent pair of loads (work item ->
+  // column pointer -> byte, an L2 round trip each) is off the path between two SNPs.
+#if TS_CODE_AHEAD
+  unsigned raw[IR];
+#pragma unroll
+  for (int j = 0; j < I; ++j) raw[j] = (valid[j] && n_items > 0) ? p.items[0].col[nj[j] >> 2] : 0u;
+#endif
+
   for (uint32_t i = 0; i < n_items; ++i) {
     const WorkItem it = p.items[i];
     const unsigned char *col = it.col;
     int code[IR];
+#if TS_CODE_AHEAD
+#pragma unroll
+    for (int j = 0; j < I; ++j) code[j] = valid[j] ? (int)((raw[j] >> (2 * (nj[j] & 3))) & 3u) : 1;
+    if (i + 1 < n_items) {
+      const unsigned char *ncol = p.items[i + 1].col;
+#pragma unroll
+      for (int j = 0; j < I; ++j)
+        if (valid[j]) raw[j] = ncol[nj[j] >> 2];
+    }
+#else
 #pragma unroll
     for (int j = 0; j < I; ++j) code[j] = valid[j] ? tsm::plink_code(col, nj[j]) : 1;
+#endif
     unsigned scode = 0;  // TIER: codes of the shared-memory tier, 2 bits per individual
     if constexpr (TIER) {
       for (int j = 0; j < J; ++j) {
@@ -359,9 +418,11 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
     if (i + 1 < n_items) {  // next SNP's genotype column and lambda row -> L2
       const WorkItem nx = p.items[i + 1];
       if constexpr (!TIER) {
+#if !TS_CODE_AHEAD
 #pragma unroll
         for (int j = 0; j < I; ++j)
           if (valid[j] && (nj[j] & 511) == 0) prefetch_l2(nx.col + (nj[j] >> 2));  // one per 128-byte line
+#endif
       } else {
         for (uint32_t n = gtid * 512u; n < p.n_local; n += GT * 512u) prefetch_l2(nx.col + (n >> 2));
       }
@@ -590,7 +651,7 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
         for (int ww = 0; ww < WS - 1; ++ww) { hi += sh[ww]; lo += sl[ww]; }
         tsfx::normalize(hi, lo);  // the low word becomes [0, 2^44)
         red_add(&st->acc[par][v][0], (unsigned long long)hi + (1ull << FX_CNT_SHIFT));
-        red_add(&st->acc[par][V + v][0], (unsigned long long)lo + (1ull << FX_CNT_SHIFT));
+        red_add(TS_LO(st->acc, par, v), (unsigned long long)lo + (1ull << FX_CNT_SHIFT));
       }
       TS_TRACE(2 + 8 * x + 3);
       // Row hand-off, both sides off the critical path.  Writer: the lanes of CTA 0 that stored the rows of
@@ -631,8 +692,9 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
                 while (true) {
                   bool complete = false;
                   for (int t = 0; t < POLL_BURST; ++t) {
-                    dh = ld_relaxed(&st->acc[par][v][0]) - bh;
-                    dl = ld_relaxed(&st->acc[par][V + v][0]) - bl;
+                    poll_pair(&st->acc[par][v][0], TS_LO(st->acc, par, v), dh, dl);
+                    dh -= bh;
+                    dl -= bl;
                     if ((dh >> FX_CNT_SHIFT) == G && (dl >> FX_CNT_SHIFT) == G) { complete = true; break; }
                   }
                   if (complete) break;
@@ -647,11 +709,11 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
                 const unsigned long long one = 1ull << FX_CNT_SHIFT;
                 if (xmode == XMODE_MCACC) {
                   mm_red_add(&p.pst_mc->gacc[par][v][0], one + dh);
-                  mm_red_add(&p.pst_mc->gacc[par][V + v][0], one + dl);
+                  mm_red_add(TS_LO(p.pst_mc->gacc, par, v), one + dl);
                 } else {
                   for (int r = 0; r < nranks; ++r) {
                     red_add_sys(&p.pst_peer[r]->gacc[par][v][0], one + dh);
-                    red_add_sys(&p.pst_peer[r]->gacc[par][V + v][0], one + dl);
+                    red_add_sys(TS_LO(p.pst_peer[r]->gacc, par, v), one + dl);
                   }
                 }
                 if (q == 0) TS_TRACE(83 + 2 * x);  // forwarded
@@ -661,8 +723,9 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
               while (true) {
                 bool complete = false;
                 for (int t = 0; t < POLL_BURST; ++t) {
-                  dh = ld_relaxed_sys(&st->gacc[par][v][0]) - bh;
-                  dl = ld_relaxed_sys(&st->gacc[par][V + v][0]) - bl;
+                  poll_pair_sys(&st->gacc[par][v][0], TS_LO(st->gacc, par, v), dh, dl);
+                  dh -= bh;
+                  dl -= bl;
                   if ((dh >> FX_CNT_SHIFT) == want && (dl >> FX_CNT_SHIFT) == want) { complete = true; break; }
                 }
                 if (complete) break;
@@ -677,8 +740,9 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
               while (true) {
                 bool complete = false;
                 for (int t = 0; t < POLL_BURST; ++t) {
-                  dh = ld_relaxed(&st->acc[par][v][0]) - bh;
-                  dl = ld_relaxed(&st->acc[par][V + v][0]) - bl;
+                  poll_pair(&st->acc[par][v][0], TS_LO(st->acc, par, v), dh, dl);
+                  dh -= bh;
+                  dl -= bl;
                   if ((dh >> FX_CNT_SHIFT) == G && (dl >> FX_CNT_SHIFT) == G) { complete = true; break; }
                 }
                 if (complete) break;
