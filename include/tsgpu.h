@@ -179,19 +179,20 @@ int ts_comm_connect_local(ts_engine **engines, int n);
  * rank_ptrs[nranks] (rank order, own rank included) and, optionally, a multicast pointer that
  * aliases the same offsets of ALL ranks' buffers (e.g. torch.distributed._symmetric_memory:
  * empty() + rendezvous() give buffer_ptrs and multicast_ptr).  The engine's exchange state moves into
- * its own buffer.  Exchange schemes (ts_comm_mode; TSGPU_XCHG in the environment forces one): with a
- * multicast pointer the default is "mcacc" -- CTA 0 adds the GPU's totals into an accumulator on every rank
- * with ONE multimem.red per word, every CTA polls one local word pair; without, "gacc" -- the same with one
- * NVLink red.add per peer (also what ts_comm_connect uses).  "slots" = the round-1 slot exchange, "mcslot" =
- * slots written with one multimem.st, "mcred" = multimem.red from every CTA (measurements:
+ * its own buffer.  Exchange schemes (ts_comm_mode; TSGPU_XCHG=gacc in the environment forces the second):
+ * with a multicast pointer the default is "mcacc" -- on every GPU the CTA whose arrival completes a word (the
+ * arrival is an atomic with return value) adds the GPU's total into an accumulator on every rank with ONE
+ * multimem.red, every CTA polls one local word pair; without, "gacc" -- the same with one NVLink red.add per
+ * peer (also what ts_comm_connect uses).  The schemes measured and rejected (slots written by every GPU, with
+ * peer stores or one multimem.st; multimem.red from every CTA; a polling CTA 0 that forwards) are described in
  * profiles/r2_summary.md).  Call it on every rank, then
  * synchronise the ranks (a host barrier) before the first ts_steps.  total_ctas = sum of the ranks'
  * CTA counts (ts_get_plan), or 0 when all shards have this engine's geometry.  ts_comm_connect_local does
  * all of this by itself for the engines of one process when the devices support multicast. */
 uint64_t ts_comm_state_bytes(void);
-/* Exchange scheme in use: 0 peer stores into slots, 1 NVLS multicast store into slots, 2 NVLS
- * in-switch reduction (multimem.red from every CTA), 3 CTA 0 adds the GPU totals into an accumulator
- * on every rank with NVLink red.add (the default), 4 the same with one multimem.red per word. */
+/* Exchange scheme in use: 3 = the last local arrival adds the GPU's totals into an accumulator on every rank
+ * with one NVLink red.add per peer ("gacc"), 4 = the same with one multimem.red per word ("mcacc"); 0-2 were
+ * the schemes of earlier builds and are no longer returned. */
 int ts_comm_mode(const ts_engine *e);
 int ts_comm_attach_symmetric(ts_engine *e, const void *const *rank_ptrs, void *multicast_ptr, uint64_t bytes,
                              uint32_t total_ctas);

@@ -52,18 +52,17 @@ struct Xbuf {
 
 // State of the persistent kernel's fence-free grid barrier (ts_persist.cuh).
 struct PState {
-  // [round parity][word = (hi|lo) * 2K + statistic][0]: monotonic fixed-point accumulators, one per
-  // 1 KB so that the 4K words of a round spread over the L2 slices
+  // [round parity][statistic][0 = high word, 1 = low word]: monotonic fixed-point accumulators, one 16-byte
+  // pair per KB so that the 2K pairs of a round spread over the L2 slices (the upper half of the middle index
+  // is unused)
   unsigned long long acc[2][4 * MAXK][128];
-  unsigned long long prev[2][4 * MAXK];        // totals at the end of the previous launch
-  // [source rank][parity][statistic][hi|lo]: a GPU's totals are 2K adjacent 16-byte pairs, so the
-  // control warp's stores to a peer (and its polls) coalesce into a few 128-byte NVLink packets
-  unsigned long long slot[MAXR][2][2 * MAXK][2];
-  unsigned long long round_ctr;                // rounds run so far (slot tags; same on every rank)
+  unsigned long long prev[2][4 * MAXK];        // [set][hi: v, lo: 2K + v] word values at the end of the previous launch
+  unsigned long long round_ctr;                // rounds run so far (the parity of the word set in use; same on every rank)
   uint32_t fault;
   uint32_t pad;
-  // XMODE_GACC / XMODE_MCACC: accumulators of the GPUs' totals, replicated on every rank (same layout as acc;
-  // the count bits count ranks), and their totals at the end of the previous launch
+  // several ranks (XMODE_GACC / XMODE_MCACC): accumulators of the GPUs' totals, replicated on every rank (same
+  // layout as acc; the top 6 bits count ranks, ts_persist.cuh GX_CNT_SHIFT), and their values at the end of the
+  // previous launch
   unsigned long long gacc[2][4 * MAXK][128];
   unsigned long long gprev[2][4 * MAXK];
 };

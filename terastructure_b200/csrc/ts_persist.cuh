@@ -41,9 +41,6 @@
 #define TS_OPTS 0
 #endif
 #define TS_OPT_NOFENCE ((TS_OPTS) & 8)
-#ifndef TS_PAIR_WORDS   // 1: the two words of a statistic are adjacent and polled with one 16-byte load
-#define TS_PAIR_WORDS 1
-#endif
 #ifndef TS_CODE_AHEAD   // 1: the register tier's genotype bytes are loaded one SNP ahead
 #define TS_CODE_AHEAD 1
 #endif
@@ -54,17 +51,23 @@
 #define TS_TIER_I 2
 #endif
 
-// address of the low word of statistic v in an accumulator array a[2][4 MAXK][128] (the high word is a[par][v][0])
-#if TS_PAIR_WORDS
+// The two words of statistic v in an accumulator array a[2][4 MAXK][128] are adjacent (one 16-byte pair per KB, the
+// pairs of a round spread over the L2 slices): the high word is a[par][v][0], the low word a[par][v][1]; one 16-byte
+// load polls both.
 #define TS_LO(a, par, v) (&(a)[par][v][1])
-#else
-#define TS_LO(a, par, v) (&(a)[par][V + (v)][0])
-#endif
+// Several GPUs: nobody polls the LOCAL words (arrivals are atomics with return value), and a word's 148 atomics are
+// served one after the other by its L2 slice -- there the low words live a slice apart from the high words (the
+// upper half of the middle index), which halves the queue in front of the last arrival's return value.
+#define TS_LO_MG(a, par, v) (&(a)[par][V + (v)][0])
 
 namespace tsp {
 
 constexpr int FX_CNT_SHIFT = tsfx::CNT_SHIFT;
 constexpr unsigned long long FX_MASK = tsfx::MASK;
+// The ranks' accumulators (PState::gacc) count RANKS in their top bits (6 bits: up to 63) and carry a GPU's totals
+// unfolded: the low words of a GPU's CTAs add up to 148 x 2^44 and those of eight GPUs to 2^54.3 -- 58 data bits.
+constexpr int GX_CNT_SHIFT = 58;
+constexpr unsigned long long GX_MASK = (1ull << GX_CNT_SHIFT) - 1;
 
 // one level of the transposed reduction: lanes whose `bit` is clear keep the low half of the
 // N live values, the others the high half; each lane adds what its partner held of its half.
@@ -96,11 +99,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long lon
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 // 16-byte (hi, lo) pair in one access; each word carries its own arrival count, so a torn pair is harmless
 __device__ __forceinline__ void ld_pair(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
@@ -108,27 +106,13 @@ __device__ __forceinline__ void ld_pair(const unsigned long long *p, unsigned lo
 __device__ __forceinline__ void ld_pair_sys(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
   asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
-// one poll of a statistic's two words
-__device__ __forceinline__ void poll_pair(const unsigned long long *ph, const unsigned long long *pl, unsigned long long &h, unsigned long long &l) {
-#if TS_PAIR_WORDS
-  (void)pl;
-  ld_pair(ph, h, l);
-#else
-  h = ld_relaxed(ph);
-  l = ld_relaxed(pl);
-#endif
-}
-__device__ __forceinline__ void poll_pair_sys(const unsigned long long *ph, const unsigned long long *pl, unsigned long long &h, unsigned long long &l) {
-#if TS_PAIR_WORDS
-  (void)pl;
-  ld_pair_sys(ph, h, l);
-#else
-  h = ld_relaxed_sys(ph);
-  l = ld_relaxed_sys(pl);
-#endif
-}
 __device__ __forceinline__ void red_add(unsigned long long *p, unsigned long long v) {
   asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long atom_add(unsigned long long *p, unsigned long long v) {  // returns the old value
+  unsigned long long o;
+  asm volatile("atom.relaxed.gpu.global.add.u64 %0, [%1], %2;" : "=l"(o) : "l"(p), "l"(v) : "memory");
+  return o;
 }
 __device__ __forceinline__ void red_add_sys(unsigned long long *p, unsigned long long v) {  // also into a peer's memory
   asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -217,8 +201,7 @@ __host__ __device__ constexpr int persist_tmax(int, int) { return 256; }
 // shared memory without the E tier, for a kernel compiled for at most T threads per CTA (multiple of 16 bytes):
 // the round's working set, then the control path's coefficient table (ts_ftab.cuh)
 __host__ __device__ constexpr size_t persist_smem_work_bytes(int K, int T) {
-  return (sizeof(double) * ((12 + 2 * RING) * K) + sizeof(long long) * (4 * K * (T / 32 + 1)) + 16 + sizeof(uint32_t) * RING +
-          sizeof(long long) * (8 * K) + 15) / 16 * 16;
+  return (sizeof(double) * ((12 + 2 * RING) * K) + sizeof(long long) * (4 * K * (T / 32 + 1)) + 16 + sizeof(uint32_t) * RING + 15) / 16 * 16;
 }
 __host__ __device__ constexpr size_t persist_smem_bytes(int K, int T) { return persist_smem_work_bytes(K, T) + FTAB_BYTES; }
 // bytes of shared-memory E tier per individual-per-thread slot
@@ -276,7 +259,6 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
   long long *s_fix = reinterpret_cast<long long *>(s_ring + RING * V);  // [NW][WS] per-warp fixed-point words
   int *s_flag = reinterpret_cast<int *>(s_fix + NW * WS);  // bit 0: round loop done, bit 1: abort
   uint32_t *s_ring_loc = reinterpret_cast<uint32_t *>(s_flag + 4);  // [RING]: locus of a ring slot, ~0 = empty
-  unsigned long long *s_lprev = reinterpret_cast<unsigned long long *>(s_ring_loc + RING);  // [2][NW] CTA 0, GACC modes: local totals so far
   double *s_tab = reinterpret_cast<double *>(smem_raw + persist_smem_work_bytes(K, TM));  // [FTAB_NI][FTAB_STRIDE]: f and 1/f
   double *s_E = reinterpret_cast<double *>(smem_raw + persist_smem_bytes(K, TM));  // TIER: [J][K][blockDim.x]
 
@@ -298,8 +280,11 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
   int tr_start, tr_len;
   tsfx::tr_slot<V>(lane, tr_start, tr_len);
 
-  // control-warp state: previous totals of the two word sets, current lambda row
+  // control-warp state: previous totals of the two word sets it polls (the local words on one GPU, the ranks'
+  // accumulators on several), current lambda row; on several GPUs also the local words' values before the round's
+  // first arrival (lh/ll: what an arrival compares the atomic's return value with to learn that it is the last)
   unsigned long long ph0[VPL], pl0[VPL], ph1[VPL], pl1[VPL];
+  unsigned long long lh0[VPL], ll0[VPL], lh1[VPL], ll1[VPL];
   double lam[VPL];
   unsigned long long rc = st->round_ctr;
   const int nranks = MG ? p.nranks : 1, xmode = MG ? p.xmode : XMODE_GACC;
@@ -309,19 +294,15 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
     for (int q = 0; q < VPL; ++q) {
       const int v = lane + 32 * q;
       const bool act = v < V;
-      // the totals this lane has seen so far on the words it polls: the GPUs' accumulators in the GACC
-      // modes (CTA 0 keeps the local words' totals in shared memory then), the local words otherwise
       const unsigned long long(*pv)[4 * MAXK] = gacc_mode ? st->gprev : st->prev;
       ph0[q] = act ? pv[0][v] : 0;
       pl0[q] = act ? pv[0][V + v] : 0;
       ph1[q] = act ? pv[1][v] : 0;
       pl1[q] = act ? pv[1][V + v] : 0;
-      if (gacc_mode && blockIdx.x == 0 && act) {
-        s_lprev[v] = st->prev[0][v];
-        s_lprev[V + v] = st->prev[0][V + v];
-        s_lprev[NW + v] = st->prev[1][v];
-        s_lprev[NW + V + v] = st->prev[1][V + v];
-      }
+      lh0[q] = (gacc_mode && act) ? st->prev[0][v] : 0;
+      ll0[q] = (gacc_mode && act) ? st->prev[0][V + v] : 0;
+      lh1[q] = (gacc_mode && act) ? st->prev[1][v] : 0;
+      ll1[q] = (gacc_mode && act) ? st->prev[1][V + v] : 0;
       lam[q] = 1024.0;  // idle lanes hold a large dummy so they never take f's small-argument path
     }
   }
@@ -644,14 +625,48 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
       TS_TRACE(2 + 8 * x + 1);
       __syncthreads();
       TS_TRACE(2 + 8 * x + 2);
-      for (int v = tid; v < V; v += blockDim.x) {  // add the warps' words, publish with arrival count 1
-        const long long *sh = s_fix + v * WS, *sl = s_fix + (V + v) * WS;
-        long long hi = 0, lo = 0;
+      if constexpr (!MG) {
+        for (int v = tid; v < V; v += blockDim.x) {  // add the warps' words, publish with arrival count 1
+          const long long *sh = s_fix + v * WS, *sl = s_fix + (V + v) * WS;
+          long long hi = 0, lo = 0;
 #pragma unroll
-        for (int ww = 0; ww < WS - 1; ++ww) { hi += sh[ww]; lo += sl[ww]; }
-        tsfx::normalize(hi, lo);  // the low word becomes [0, 2^44)
-        red_add(&st->acc[par][v][0], (unsigned long long)hi + (1ull << FX_CNT_SHIFT));
-        red_add(TS_LO(st->acc, par, v), (unsigned long long)lo + (1ull << FX_CNT_SHIFT));
+          for (int ww = 0; ww < WS - 1; ++ww) { hi += sh[ww]; lo += sl[ww]; }
+          tsfx::normalize(hi, lo);  // the low word becomes [0, 2^44)
+          red_add(&st->acc[par][v][0], (unsigned long long)hi + (1ull << FX_CNT_SHIFT));
+          red_add(TS_LO(st->acc, par, v), (unsigned long long)lo + (1ull << FX_CNT_SHIFT));
+        }
+      } else if (warp == 0) {
+        // Several GPUs: the arrival is an atomic WITH return value.  The CTA whose addition completes a word (G - 1
+        // arrivals before it) holds the GPU's total of that word and forwards it at once into every rank's
+        // accumulator -- with one multimem.red where an NVLS alias exists, one NVLink red.add per peer otherwise.
+        // No CTA waits for the local words: the detection of "all local CTAs arrived" by a polling CTA 0 (half to
+        // one and a half L2 round trips) is replaced by the return trip of the last arrival's own atomic.
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+          const int v = lane + 32 * q;
+          if (v < V) {
+            const long long *sh = s_fix + v * WS, *sl = s_fix + (V + v) * WS;
+            long long hi = 0, lo = 0;
+#pragma unroll
+            for (int ww = 0; ww < WS - 1; ++ww) { hi += sh[ww]; lo += sl[ww]; }
+            tsfx::normalize(hi, lo);
+            const unsigned long long one = 1ull << FX_CNT_SHIFT, gone = 1ull << GX_CNT_SHIFT;
+            const unsigned long long oh = atom_add(&st->acc[par][v][0], (unsigned long long)hi + one) - (par ? lh1[q] : lh0[q]);
+            const unsigned long long ol = atom_add(TS_LO_MG(st->acc, par, v), (unsigned long long)lo + one) - (par ? ll1[q] : ll0[q]);
+            const bool last_h = (oh >> FX_CNT_SHIFT) == G - 1, last_l = (ol >> FX_CNT_SHIFT) == G - 1;
+            const unsigned long long th = gone + (oh & FX_MASK) + (unsigned long long)hi, tl = gone + (ol & FX_MASK) + (unsigned long long)lo;
+            if (xmode == XMODE_MCACC) {
+              if (last_h) mm_red_add(&p.pst_mc->gacc[par][v][0], th);
+              if (last_l) mm_red_add(TS_LO(p.pst_mc->gacc, par, v), tl);
+            } else if (last_h || last_l) {
+              for (int r = 0; r < nranks; ++r) {
+                if (last_h) red_add_sys(&p.pst_peer[r]->gacc[par][v][0], th);
+                if (last_l) red_add_sys(TS_LO(p.pst_peer[r]->gacc, par, v), tl);
+              }
+            }
+          }
+        }
+        __syncwarp();
       }
       TS_TRACE(2 + 8 * x + 3);
       // Row hand-off, both sides off the critical path.  Writer: the lanes of CTA 0 that stored the rows of
@@ -687,60 +702,35 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
             // the GPU's totals into every rank's accumulator); the other CTAs wait for the accumulator alone,
             // which keeps the pollers off the words the arrivals are being added to.
             if (gacc_mode) {
-              if (blockIdx.x == 0) {  // this GPU's totals (local words complete) -> every rank's accumulator
-                const unsigned long long bh = s_lprev[par * NW + v], bl = s_lprev[par * NW + V + v];
-                while (true) {
-                  bool complete = false;
-                  for (int t = 0; t < POLL_BURST; ++t) {
-                    poll_pair(&st->acc[par][v][0], TS_LO(st->acc, par, v), dh, dl);
-                    dh -= bh;
-                    dl -= bl;
-                    if ((dh >> FX_CNT_SHIFT) == G && (dl >> FX_CNT_SHIFT) == G) { complete = true; break; }
-                  }
-                  if (complete) break;
-                  if (guard.expired(p.timeout_ns)) { abort = true; break; }
-                }
-                s_lprev[par * NW + v] = bh + dh;
-                s_lprev[par * NW + V + v] = bl + dl;
-                dh &= FX_MASK;
-                dl &= FX_MASK;
-                tsfx::fold(dh, dl);  // low word below 2^44 again: the sum over the ranks stays inside the data bits
-                if (q == 0) TS_TRACE(82 + 2 * x);  // local words complete
-                const unsigned long long one = 1ull << FX_CNT_SHIFT;
-                if (xmode == XMODE_MCACC) {
-                  mm_red_add(&p.pst_mc->gacc[par][v][0], one + dh);
-                  mm_red_add(TS_LO(p.pst_mc->gacc, par, v), one + dl);
-                } else {
-                  for (int r = 0; r < nranks; ++r) {
-                    red_add_sys(&p.pst_peer[r]->gacc[par][v][0], one + dh);
-                    red_add_sys(TS_LO(p.pst_peer[r]->gacc, par, v), one + dl);
-                  }
-                }
-                if (q == 0) TS_TRACE(83 + 2 * x);  // forwarded
-              }
-              // every CTA: one word pair per statistic, complete when every rank has added its totals
+              // every CTA: one word pair per statistic, complete when every rank's last arrival has added its GPU's totals
               const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q], want = (unsigned long long)nranks;
               while (true) {
                 bool complete = false;
                 for (int t = 0; t < POLL_BURST; ++t) {
-                  poll_pair_sys(&st->gacc[par][v][0], TS_LO(st->gacc, par, v), dh, dl);
+                  ld_pair_sys(&st->gacc[par][v][0], dh, dl);
                   dh -= bh;
                   dl -= bl;
-                  if ((dh >> FX_CNT_SHIFT) == want && (dl >> FX_CNT_SHIFT) == want) { complete = true; break; }
+                  if ((dh >> GX_CNT_SHIFT) == want && (dl >> GX_CNT_SHIFT) == want) { complete = true; break; }
                 }
                 if (complete) break;
                 if (guard.expired(p.timeout_ns)) { abort = true; break; }
               }
               if (par) { ph1[q] = bh + dh; pl1[q] = bl + dl; } else { ph0[q] = bh + dh; pl0[q] = bl + dl; }
-              dh &= FX_MASK;
-              dl &= FX_MASK;
-              tsfx::fold(dh, dl);
+              dh &= GX_MASK;
+              dl &= GX_MASK;
+              tsfx::fold(dh, dl);  // the low words of all CTAs of all ranks: carry first (to_double wants both below 2^52)
+              // The local words of this set are final now (every rank forwarded, so this GPU's last arrival happened):
+              // their values are the base of the set's next use, two rounds from now.  The loads go straight into the
+              // registers of that use; nothing touches them before, so the round does not wait for them.  (They are
+              // issued a full round -- a grid barrier and an NVLink round trip -- before any CTA can arrive on the set again.)
+              if (par) { lh1[q] = ld_relaxed(&st->acc[par][v][0]); ll1[q] = ld_relaxed(TS_LO_MG(st->acc, par, v)); }
+              else { lh0[q] = ld_relaxed(&st->acc[par][v][0]); ll0[q] = ld_relaxed(TS_LO_MG(st->acc, par, v)); }
             } else {
               const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q];
               while (true) {
                 bool complete = false;
                 for (int t = 0; t < POLL_BURST; ++t) {
-                  poll_pair(&st->acc[par][v][0], TS_LO(st->acc, par, v), dh, dl);
+                  ld_pair(&st->acc[par][v][0], dh, dl);
                   dh -= bh;
                   dl -= bl;
                   if ((dh >> FX_CNT_SHIFT) == G && (dl >> FX_CNT_SHIFT) == G) { complete = true; break; }
@@ -849,10 +839,10 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
         pv[1][v] = ph1[q];
         pv[1][V + v] = pl1[q];
         if (gacc_mode) {
-          st->prev[0][v] = s_lprev[v];
-          st->prev[0][V + v] = s_lprev[V + v];
-          st->prev[1][v] = s_lprev[NW + v];
-          st->prev[1][V + v] = s_lprev[NW + V + v];
+          st->prev[0][v] = lh0[q];
+          st->prev[0][V + v] = ll0[q];
+          st->prev[1][v] = lh1[q];
+          st->prev[1][V + v] = ll1[q];
         }
       }
     }

@@ -10,23 +10,21 @@ from . import capi
 
 _keepalive = []  # symmetric buffers must outlive the engines that use them
 
-MODES = {0: "CTA 0 stores the GPU totals into its slot on every peer, every CTA polls the rank slots",
-         1: "NVLS multicast store of the GPU totals (multimem.st), slots polled locally",
-         2: "NVLS in-switch reduction: multimem.red.add.u64 from every CTA of every GPU",
-         3: "CTA 0 adds the GPU totals into an accumulator on every rank (NVLink red.add.u64), every CTA polls one local word pair",
-         4: "CTA 0 adds the GPU totals with one multimem.red.add.u64 per word (NVLS), every CTA polls one local word pair"}
+MODES = {3: "the CTA whose arrival completes a word (atomic with return value) adds the GPU's total into an accumulator on "
+            "every rank (one NVLink red.add.u64 per peer), every CTA polls one local word pair",
+         4: "the CTA whose arrival completes a word (atomic with return value) adds the GPU's total into every rank's "
+            "accumulator with one multimem.red.add.u64 (NVLS), every CTA polls one local word pair"}
 
 
 def connect(engine, group=None):
     """Connect `engine` (rank, nranks as created) with its peers in `group` (default: WORLD).
 
-    Default: a torch symmetric-memory buffer with its NVLS multicast alias (ts_comm_attach_symmetric): CTA 0
-    of every GPU adds the GPU's totals into an accumulator on every rank with ONE multimem.red per word and
-    every CTA polls one local word pair (XMODE_MCACC, the fastest scheme measured: profiles/r2_summary.md).
-    Without symmetric memory / NVLS, or with TSGPU_XCHG=gacc|slots|ipc: CUDA-IPC handles of the engines' own
-    buffers (ts_comm_export / ts_comm_connect) and one NVLink red.add per peer (XMODE_GACC), or the round-1
-    slot exchange (slots).  Returns a dict describing what was set up; ends with a barrier, so ts_steps may
-    follow immediately."""
+    Default: a torch symmetric-memory buffer with its NVLS multicast alias (ts_comm_attach_symmetric): on every
+    GPU the CTA whose arrival completes a word adds the GPU's total into an accumulator on every rank with ONE
+    multimem.red and every CTA polls one local word pair (XMODE_MCACC, the fastest scheme measured:
+    profiles/r2_summary.md).  Without symmetric memory / NVLS, or with TSGPU_XCHG=gacc: CUDA-IPC handles of the
+    engines' own buffers (ts_comm_export / ts_comm_connect) and one NVLink red.add per peer (XMODE_GACC).
+    Returns a dict describing what was set up; ends with a barrier, so ts_steps may follow immediately."""
     import torch
     import torch.distributed as dist
     group = group or dist.group.WORLD

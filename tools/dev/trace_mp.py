@@ -31,13 +31,13 @@ if rank == 0:
     t = e.debug_trace().astype(np.float64)
     it = t[8:60]
     def d(a, b): return np.mean(it[:, b] - it[:, a])
-    acc = np.zeros(9)
+    acc = np.zeros(7)
     for x in range(9):  # rounds 0..8 (the last one hides the gamma step)
         base = 2 + 8 * x
         prev = (2 + 8 * (x - 1) + 6) if x else 1
         acc += np.array([d(prev, base), d(base, base + 1), d(base + 1, base + 2), d(base + 2, base + 3),
-                         d(base + 3, 82 + 2 * x), d(82 + 2 * x, 83 + 2 * x), d(83 + 2 * x, base + 4), d(base + 4, base + 5), d(base + 5, base + 6)])
-    names = ["E-step", "tr_reduce", "sync1", "CTA-sum+publish", "local barrier", "peer stores", "wait rank slots", "lambda/b", "sync2"]
+                         d(base + 3, base + 4), d(base + 4, base + 5), d(base + 5, base + 6)])
+    names = ["E-step", "tr_reduce", "sync1", "CTA-sum + arrival (atomic with return, forward if last)", "wait for the ranks", "lambda/b", "sync2"]
     print("mean/round (rounds 0-8): " + "  ".join("%s %.0f" % (nm, v / 9) for nm, v in zip(names, acc)) + "  total %.0f" % (acc.sum() / 9))
     print("whole item %.0f cycles" % np.mean(it[1:, 0] - it[:-1, 0]))
     sys.stdout.flush()
