@@ -41,6 +41,14 @@
 #define TS_OPTS 0
 #endif
 #define TS_OPT_NOFENCE ((TS_OPTS) & 8)
+// One GPU: cycles between a CTA's arrival and its first poll.  Polls that come back incomplete are not free: the
+// word's L2 slice serves the 148 CTAs' loads and arrivals one after the other.  Measured on two B200s, us per SVI
+// iteration at 100 000 individuals: first poll at once 27.75 / 30.07, after 200 cycles - / 28.71, 300: 27.16 / 28.32,
+// 400: 26.90 / 28.03, 500: 26.96, 600: 27.41; a pause between polls (fixed, or in proportion to the arrivals still
+// missing) and a second poll in flight half a round trip later all lose (profiles/r2_summary.md).
+#ifndef TS_POLL_DELAY
+#define TS_POLL_DELAY 400
+#endif
 #ifndef TS_CODE_AHEAD   // 1: the register tier's genotype bytes are loaded one SNP ahead
 #define TS_CODE_AHEAD 1
 #endif
@@ -727,6 +735,9 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
               else { lh0[q] = ld_relaxed(&st->acc[par][v][0]); ll0[q] = ld_relaxed(TS_LO_MG(st->acc, par, v)); }
             } else {
               const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q];
+#if TS_POLL_DELAY > 0
+              if (q == 0 && G > 32) { const long long t0 = clock64(); while (clock64() - t0 < TS_POLL_DELAY) {} }  // small grids complete at once
+#endif
               while (true) {
                 bool complete = false;
                 for (int t = 0; t < POLL_BURST; ++t) {
