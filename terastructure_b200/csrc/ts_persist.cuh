@@ -45,10 +45,12 @@
 // word's L2 slice serves the 148 CTAs' loads and arrivals one after the other.  Measured on two B200s, us per SVI
 // iteration at 100 000 individuals: first poll at once 27.75 / 30.07, after 200 cycles - / 28.71, 300: 27.16 / 28.32,
 // 400: 26.90 / 28.03, 500: 26.96, 600: 27.41; a pause between polls (fixed, or in proportion to the arrivals still
-// missing) and a second poll in flight half a round trip later all lose (profiles/r2_summary.md).
+// missing) and a second poll in flight half a round trip later all lose; with the delay in place the pairs still beat
+// low words a slice apart from the high words (26.90 against 27.04) (profiles/r2_summary.md).
 #ifndef TS_POLL_DELAY
 #define TS_POLL_DELAY 400
 #endif
+
 #ifndef TS_CODE_AHEAD   // 1: the register tier's genotype bytes are loaded one SNP ahead
 #define TS_CODE_AHEAD 1
 #endif
