@@ -528,13 +528,14 @@ def main():
                                          "capture of this instantiation and shard size (profiles/r2_ncu_metrics.json); "
                                          "null = no capture of this geometry",
                          "peak_source": peak_src,
-                         "kernel": "tsp::k_persist<%d,%d>, %d CTAs x %d threads (one cooperative launch per step = %d SVI iterations)"
-                                   % (K, ipt, grid, block, BATCH),
+                         "kernel": "tsp::k_persist<%d,%d,%s,%s> (K, individuals per thread in registers, tiered, several GPUs), "
+                                   "%d CTAs x %d threads (one cooperative launch per step = %d SVI iterations)"
+                                   % (K, ipt, "true" if eng.tiers[0] >= 0 else "false", "true" if world > 1 else "false", grid, block, BATCH),
                          "algorithmic_bytes_per_genotype": bpg,
                          "fp64_pipe_pct": prof["fp64_pipe_pct"] if prof else None,
                          "fp64_note": "sm__pipe_fp64_cycles_active (% of peak) from the same capture; the path is bound by the "
                                       "latency of 10 dependent grid-wide reductions per SVI iteration, not by HBM or FP64 "
-                                      "(DESIGN.md section 6); FP64 ceiling of this algorithm = 0.67 of the HBM roofline"},
+                                      "(DESIGN.md section 4.1); FP64 ceiling of this algorithm = 0.67 of the HBM roofline"},
             "wall_s_timed_region": t_wall, "mean_rounds_per_snp": mean_rounds,
             "us_per_svi_iteration": us_iter,
             "parity_check": parity,
