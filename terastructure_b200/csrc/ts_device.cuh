@@ -51,6 +51,8 @@ struct Xbuf {
 };
 
 // State of the persistent kernel's fence-free grid barrier (ts_persist.cuh).
+constexpr int MG_SUB_MAX = 8;
+
 struct PState {
   // [round parity][statistic][0 = high word, 1 = low word]: monotonic fixed-point accumulators, one 16-byte
   // pair per KB so that the 2K pairs of a round spread over the L2 slices (the upper half of the middle index
@@ -65,6 +67,10 @@ struct PState {
   // previous launch
   unsigned long long gacc[2][4 * MAXK][128];
   unsigned long long gprev[2][4 * MAXK];
+  // several ranks: the local words come in MG_SUB copies 128 bytes apart (acc[par][word][16 s]); the CTAs whose
+  // index is s modulo MG_SUB arrive on copy s, and each copy's last arrival forwards the copy's total.  Values of the
+  // copies at the end of the previous launch (copy 0 lives in prev):
+  unsigned long long lprev[MG_SUB_MAX][2][4 * MAXK];
 };
 
 // Everything a peer GPU writes into lives in one allocation (one IPC handle).

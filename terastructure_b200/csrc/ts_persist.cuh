@@ -51,6 +51,13 @@
 #define TS_POLL_DELAY 400
 #endif
 
+// Several GPUs: copies of the local words, each receiving the arrivals of the CTAs with index s modulo TS_MG_SUB.  The
+// arrival is an atomic with return value, and a word's atomics are served one after the other by its L2 slice: with
+// 148 CTAs on one word the last arrival's return value -- the moment the GPU's total can be forwarded -- is ~1 200
+// cycles away, half of it queueing.
+#ifndef TS_MG_SUB
+#define TS_MG_SUB 4
+#endif
 #ifndef TS_CODE_AHEAD   // 1: the register tier's genotype bytes are loaded one SNP ahead
 #define TS_CODE_AHEAD 1
 #endif
@@ -74,8 +81,9 @@ namespace tsp {
 
 constexpr int FX_CNT_SHIFT = tsfx::CNT_SHIFT;
 constexpr unsigned long long FX_MASK = tsfx::MASK;
-// The ranks' accumulators (PState::gacc) count RANKS in their top bits (6 bits: up to 63) and carry a GPU's totals
-// unfolded: the low words of a GPU's CTAs add up to 148 x 2^44 and those of eight GPUs to 2^54.3 -- 58 data bits.
+// The ranks' accumulators (PState::gacc) count forwarded totals in their top 6 bits (ranks x copies of the local
+// words, at most 63) and carry the totals unfolded: the low words of a GPU's CTAs add up to 148 x 2^44 and those of
+// eight GPUs to 2^54.3 -- 58 data bits.
 constexpr int GX_CNT_SHIFT = 58;
 constexpr unsigned long long GX_MASK = (1ull << GX_CNT_SHIFT) - 1;
 
@@ -299,6 +307,14 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
   unsigned long long rc = st->round_ctr;
   const int nranks = MG ? p.nranks : 1, xmode = MG ? p.xmode : XMODE_GACC;
   constexpr bool gacc_mode = MG;  // several ranks: the replicated accumulator (XMODE_GACC / XMODE_MCACC) is the only exchange
+  // this CTA's copy of the local words, the CTAs that share it, the copies in use (all ranks run the same grid size)
+  static_assert(TS_MG_SUB >= 1 && TS_MG_SUB <= MG_SUB_MAX, "copies of the local words");
+  // Every rank adds NSUB_ALL to the count of a ranks' accumulator word per round, whatever its grid: a rank with fewer
+  // CTAs than copies lets copy 0's forward stand for the copies it does not use.
+  const unsigned NSUB_ALL = MG ? max(1u, min((unsigned)TS_MG_SUB, 63u / (unsigned)nranks)) : 1u;
+  const unsigned nsub = min(NSUB_ALL, gridDim.x), sub = blockIdx.x % nsub;
+  const unsigned long long G_sub = (gridDim.x - sub + nsub - 1) / nsub;
+  const unsigned long long fwd_count = (unsigned long long)(sub == 0 ? NSUB_ALL - nsub + 1 : 1) << GX_CNT_SHIFT;
   if (warp == 0) {
 #pragma unroll
     for (int q = 0; q < VPL; ++q) {
@@ -309,10 +325,10 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
       pl0[q] = act ? pv[0][V + v] : 0;
       ph1[q] = act ? pv[1][v] : 0;
       pl1[q] = act ? pv[1][V + v] : 0;
-      lh0[q] = (gacc_mode && act) ? st->prev[0][v] : 0;
-      ll0[q] = (gacc_mode && act) ? st->prev[0][V + v] : 0;
-      lh1[q] = (gacc_mode && act) ? st->prev[1][v] : 0;
-      ll1[q] = (gacc_mode && act) ? st->prev[1][V + v] : 0;
+      lh0[q] = (gacc_mode && act) ? st->lprev[sub][0][v] : 0;
+      ll0[q] = (gacc_mode && act) ? st->lprev[sub][0][V + v] : 0;
+      lh1[q] = (gacc_mode && act) ? st->lprev[sub][1][v] : 0;
+      ll1[q] = (gacc_mode && act) ? st->lprev[sub][1][V + v] : 0;
       lam[q] = 1024.0;  // idle lanes hold a large dummy so they never take f's small-argument path
     }
   }
@@ -660,10 +676,10 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
 #pragma unroll
             for (int ww = 0; ww < WS - 1; ++ww) { hi += sh[ww]; lo += sl[ww]; }
             tsfx::normalize(hi, lo);
-            const unsigned long long one = 1ull << FX_CNT_SHIFT, gone = 1ull << GX_CNT_SHIFT;
-            const unsigned long long oh = atom_add(&st->acc[par][v][0], (unsigned long long)hi + one) - (par ? lh1[q] : lh0[q]);
-            const unsigned long long ol = atom_add(TS_LO_MG(st->acc, par, v), (unsigned long long)lo + one) - (par ? ll1[q] : ll0[q]);
-            const bool last_h = (oh >> FX_CNT_SHIFT) == G - 1, last_l = (ol >> FX_CNT_SHIFT) == G - 1;
+            const unsigned long long one = 1ull << FX_CNT_SHIFT, gone = fwd_count;
+            const unsigned long long oh = atom_add(&st->acc[par][v][16 * sub], (unsigned long long)hi + one) - (par ? lh1[q] : lh0[q]);
+            const unsigned long long ol = atom_add(TS_LO_MG(st->acc, par, v) + 16 * sub, (unsigned long long)lo + one) - (par ? ll1[q] : ll0[q]);
+            const bool last_h = (oh >> FX_CNT_SHIFT) == G_sub - 1, last_l = (ol >> FX_CNT_SHIFT) == G_sub - 1;
             const unsigned long long th = gone + (oh & FX_MASK) + (unsigned long long)hi, tl = gone + (ol & FX_MASK) + (unsigned long long)lo;
             if (xmode == XMODE_MCACC) {
               if (last_h) mm_red_add(&p.pst_mc->gacc[par][v][0], th);
@@ -713,7 +729,7 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
             // which keeps the pollers off the words the arrivals are being added to.
             if (gacc_mode) {
               // every CTA: one word pair per statistic, complete when every rank's last arrival has added its GPU's totals
-              const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q], want = (unsigned long long)nranks;
+              const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q], want = (unsigned long long)nranks * NSUB_ALL;
               while (true) {
                 bool complete = false;
                 for (int t = 0; t < POLL_BURST; ++t) {
@@ -733,8 +749,8 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
               // their values are the base of the set's next use, two rounds from now.  The loads go straight into the
               // registers of that use; nothing touches them before, so the round does not wait for them.  (They are
               // issued a full round -- a grid barrier and an NVLink round trip -- before any CTA can arrive on the set again.)
-              if (par) { lh1[q] = ld_relaxed(&st->acc[par][v][0]); ll1[q] = ld_relaxed(TS_LO_MG(st->acc, par, v)); }
-              else { lh0[q] = ld_relaxed(&st->acc[par][v][0]); ll0[q] = ld_relaxed(TS_LO_MG(st->acc, par, v)); }
+              if (par) { lh1[q] = ld_relaxed(&st->acc[par][v][16 * sub]); ll1[q] = ld_relaxed(TS_LO_MG(st->acc, par, v) + 16 * sub); }
+              else { lh0[q] = ld_relaxed(&st->acc[par][v][16 * sub]); ll0[q] = ld_relaxed(TS_LO_MG(st->acc, par, v) + 16 * sub); }
             } else {
               const unsigned long long bh = par ? ph1[q] : ph0[q], bl = par ? pl1[q] : pl0[q];
 #if TS_POLL_DELAY > 0
@@ -841,6 +857,18 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
     TS_TRACE(101);
   }
 
+  if (gacc_mode && blockIdx.x < nsub && warp == 0) {  // the first CTA of every copy of the local words keeps the copy's values
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      const int v = lane + 32 * q;
+      if (v < V) {
+        st->lprev[sub][0][v] = lh0[q];
+        st->lprev[sub][0][V + v] = ll0[q];
+        st->lprev[sub][1][v] = lh1[q];
+        st->lprev[sub][1][V + v] = ll1[q];
+      }
+    }
+  }
   if (blockIdx.x == 0 && warp == 0) {
 #pragma unroll
     for (int q = 0; q < VPL; ++q) {
@@ -851,12 +879,6 @@ __global__ void __launch_bounds__(TIER ? TIER_THREADS : persist_tmax(K, I), 1) k
         pv[0][V + v] = pl0[q];
         pv[1][v] = ph1[q];
         pv[1][V + v] = pl1[q];
-        if (gacc_mode) {
-          st->prev[0][v] = lh0[q];
-          st->prev[0][V + v] = ll0[q];
-          st->prev[1][v] = lh1[q];
-          st->prev[1][V + v] = ll1[q];
-        }
       }
     }
     if (lane == 0) st->round_ctr = rc;
