@@ -6,22 +6,29 @@
 //
 //   per SNP:  warp 0 of every CTA: b[k][t] = f(lambda[loc][k][t]) / f(lambda[k][0]+lambda[k][1]),
 //                                  f = exp o digamma                         (estimate_beta)
+//             -- f and 1/f from piecewise polynomials in shared memory (ts_ftab.cuh): this path is
+//             one warp's dependent chain, six FP64 instructions from lambda to b
 //     per round (<= online_iterations):
 //       every thread: its individuals' E-step from REGISTERS (E = f(gamma) of up to 4 individuals
 //             per thread stays in registers for the whole launch), 4K FMA + 2 reciprocals each
 //       warp: transposed shuffle reduction of the 2K partial sums (each lane ends with one sum)
 //       CTA:  every warp converts its 2K sums to 98-bit FIXED-POINT integers (two u64 words);
-//             4K threads add the warps' words -- integer addition is associative, so the total
+//             2K threads add the warps' words -- integer addition is associative, so the total
 //             does not depend on the order of anything
-//       grid: the CTA totals are added into 4K global words with relaxed red.add; each word also
-//             counts arrivals in its top 10 bits, so the grid barrier needs no fence and no
-//             separate flag: one L2 round trip to publish, one to observe.  The words are
+//       grid: the CTA totals are added into 2K global 16-byte word pairs with relaxed red.add; each
+//             word also counts arrivals in its top 10 bits, so the grid barrier needs no fence and
+//             no separate flag: one L2 trip to publish, one round trip to observe.  The words are
 //             monotonic (never reset); two sets alternate by round parity and every CTA remembers
-//             the previous total of each set.  Lane v of the control warp spins on the two words
-//             of statistic v.  Words sit 1 KB apart so that they spread over the L2 slices.
-//       multi-GPU: CTA 0 stores the GPU's integer totals (tagged with the round number) into its
-//             slot on every peer over NVLink; every CTA of every GPU adds the slots in rank order.
-//       warp 0 of every CTA (redundantly, bit-identically): lambda, convergence test, new b
+//             the previous total of each set.  Lane v of the control warp waits 400 cycles (early
+//             polls only queue in front of the arrivals), then spins on the pair of statistic v
+//             with one 16-byte load.  Pairs sit 1 KB apart so that they spread over the L2 slices.
+//       several GPUs (template parameter MG; the single-GPU kernel has none of this code): the
+//             arrival is an atomic WITH return value on one of four copies of the local word; the
+//             CTA whose arrival completes a copy forwards the copy's total into an accumulator that
+//             is replicated on every rank (one multimem.red through NVLS, or one red.add per peer),
+//             and every CTA of every GPU polls one local pair of that accumulator.
+//       warp 0 of every CTA (redundantly, bit-identically): lambda, new b, convergence test -- the
+//             two chains interleaved in one basic block
 //     gamma step + E = f(gamma) refresh for the CTA's individuals (skipped in hol mode); when all
 //     permitted rounds run it starts right after the last round's arrivals, in the shadow of that
 //     round's barrier, and the last warp first prepares b for the next SNP's first round
@@ -35,8 +42,8 @@
 #include "ts_ftab.cuh"
 
 // Build-time switch for measurements (make lib SUFFIX=_nofence OPTS=8): bit 3 drops the fences of the
-// row hand-off (see "row hand-off" below) to price them.  Variants measured and rejected in round 2
-// (profiles/r2_summary.md): one gamma call site, preloading the next SNP's genotype codes.
+// row hand-off (see "row hand-off" below) to price them.  Variants measured and rejected in round 2:
+// profiles/r2_summary.md sections 1 and 6.
 #ifndef TS_OPTS
 #define TS_OPTS 0
 #endif
