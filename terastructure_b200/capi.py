@@ -172,9 +172,11 @@ class Engine:
     """One shard of individuals resident on one B200 (ts_engine)."""
 
     def __init__(self, n, l, k, *, device=0, rank=0, nranks=1, n_begin=0, n_local=None,
-                 online_iterations=10):
+                 online_iterations=10, eta=None):
         cfg = TsConfig()
         lib().ts_config_defaults(C.byref(cfg), n, l, k)
+        if eta is not None:  # prior of lambda (the reference hard-codes 1.0, snpsamplinge.cc:25-27)
+            cfg.eta0 = cfg.eta1 = float(eta)
         cfg.device, cfg.rank, cfg.nranks = device, rank, nranks
         cfg.n_begin = n_begin
         cfg.n_local = n if n_local is None else n_local

@@ -385,6 +385,44 @@ def test_exp_digamma_table_on_device():
     assert rel_err(e.get_lambda(), o.lam) < 1e-12
 
 
+@pytest.mark.parametrize("eta", [0.25, 1.0])
+def test_control_path_table_and_fallback_on_device(eta, tmp_path):
+    """The control warp's b = f(lambda_t) / f(lambda_0 + lambda_1) on the device: table-driven (ts_ftab.cuh) with the
+    reference's prior eta = 1, and through the analytic fallback with eta = 0.25 (lambda below 1 lies outside the
+    table's domain) -- against the host model of the same sources (tests/kernel_model.cpp), which test_kernel_model.py
+    ties to the oracle.  Same rounds, gamma and lambda to rounding (device FMA contraction and MUFU seed differ)."""
+    import ctypes as C
+    import os
+    import subprocess
+    import terastructure_b200 as ts
+    from conftest import ROOT
+    from terastructure_b200 import plink
+    so = str(tmp_path / "libkm.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "terastructure_b200", "csrc"),
+                    "-o", so, os.path.join(ROOT, "tests", "kernel_model.cpp")], check=True)
+    km = C.CDLL(so)
+    n, l, k = 3001, 120, 5
+    rs = np.random.RandomState(11)
+    y = rs.randint(0, 3, size=(l, n)).astype(np.uint8)
+    y[rs.rand(l, n) < 0.02] = 3
+    g0 = rs.gamma(100.0, 0.01, size=(n, k))
+    g0[:, k - 1] *= 1e-3   # a population nobody belongs to yet: its statistics stay near zero, lambda near eta, in every round
+    locs = np.array([5, 9, 5, 33, 9, 100, 5, 61, 61, 7], np.uint32)
+    e = ts.Engine(n, l, k, eta=eta)
+    e.load_bed(plink.pack(y))
+    e.set_gamma(g0)
+    rounds = e.steps(locs, want_rounds=True)
+    g, cnt, lam, ro = np.ascontiguousarray(g0.copy()), np.zeros(n, np.uint32), np.full((l, k, 2), eta), np.zeros(len(locs), np.uint32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    km.km_train(n, l, k, p(y), p(g), p(cnt), p(lam), p(locs), len(locs), 10, C.c_double(1e-3), C.c_double(1.0 / k),
+                C.c_double(eta), C.c_double(2.0), 3, p(ro))
+    assert rounds.tolist() == ro.tolist()
+    np.testing.assert_array_equal(e.counts, cnt)
+    assert rel_err(e.gamma, g) < 1e-11
+    assert rel_err(e.get_lambda(), lam) < 1e-11
+    assert (lam[locs].min() < 1.0) == (eta < 1.0)   # with eta = 0.25 the rows of the visited loci leave the table's domain
+
+
 def test_cli_012_input_sigterm_and_gpus(tmp_path):
     """CLI on a .012 text file (snp.cc:6-93) with missing genotypes, stopped by SIGTERM after a few
     reports like the reference (main.cc:28-39: save the model, exit 0); `-gpus 2` when two GPUs are
