@@ -6,6 +6,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -292,6 +293,14 @@ def test_exp_digamma_host_model_vs_mpmath(tmp_path):
             assert e == 0.0
     assert worst["large"] < 5e-16 and worst["mid"] < 1e-14 and worst["small"] < 3e-13, worst
     assert worst["rcp"] < 2.3e-16 and worst["exp"] < 1e-14, worst
+
+
+def test_control_path_table_is_reproducible(tmp_path):
+    """The committed coefficient table (terastructure_b200/csrc/ts_ftab.inc) is exactly what tools/gen_ftab.py writes."""
+    pytest.importorskip("mpmath")
+    out = str(tmp_path / "ts_ftab.inc")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_ftab.py"), out], check=True, capture_output=True)
+    assert open(out).read() == open(os.path.join(ROOT, "terastructure_b200", "csrc", "ts_ftab.inc")).read()
 
 
 def test_control_path_table_vs_mpmath(tmp_path):
