@@ -165,9 +165,10 @@ int ts_sync(ts_engine *e);
 
 /* ---- multi-GPU exchange (replaces the main thread's sum over workers' lambdat,
  *      snpsamplinge.cc:337-352) ------------------------------------------------------------
- * Individuals are sharded; each round every engine publishes its 2K partial sums into a
- * slot of every peer's exchange buffer by direct NVLink stores and adds the nranks slots in
- * rank order, so all ranks hold bit-identical lambda.  One process per GPU: export the
+ * Individuals are sharded; each round every engine adds its 2K partial sums, as fixed-point
+ * integers, into an accumulator in every peer's exchange buffer (NVLink atomics, or one NVLS
+ * multicast reduction), so all ranks hold bit-identical lambda whatever the order of arrival
+ * (details with ts_comm_attach_symmetric below).  One process per GPU: export the
  * local buffer as an opaque 64-byte CUDA IPC handle, all-gather the handles by any means,
  * then connect.  One process driving several GPUs: ts_comm_connect_local. */
 #define TS_COMM_HANDLE_BYTES 64
@@ -223,7 +224,9 @@ uint64_t ts_launch_count(const ts_engine *e);
 int ts_timer_start(ts_engine *e);
 int ts_timer_stop(ts_engine *e, float *ms_out);
 /* Developer aid: with TSGPU_TRACE=1 in the environment at ts_create, CTA 0 of the persistent kernel
- * stamps clock64() at its phase boundaries for the first 64 work items of a launch (64 x 128 slots). */
+ * stamps clock64() at its phase boundaries for the first 64 work items of a launch (64 x 128 slots) --
+ * in the developer build of the library only (make -C terastructure_b200/csrc trace); the product
+ * library carries no stamps and returns zeros. */
 int ts_debug_trace(ts_engine *e, long long *out);
 
 /* ---- host-side, RNG-exact initialisation (no GPU needed) ------------------------------

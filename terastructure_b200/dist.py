@@ -33,7 +33,7 @@ def connect(engine, group=None):
     if world == 1:
         return info
     want = os.environ.get("TSGPU_XCHG", "")
-    if want not in ("gacc", "slots", "ipc"):
+    if want not in ("gacc", "slots", "ipc"):  # "slots" / "ipc": names of earlier builds, now the same as "gacc"
         import torch.distributed._symmetric_memory as symm_mem
         dev = torch.device("cuda", int(engine.cfg.device))
         nbytes = int(capi.lib().ts_comm_state_bytes())
